@@ -1,0 +1,943 @@
+// B200 (sm_100a) engine of the MsFEC multiscale basis build.
+//
+// Data layout.  Coarse cells are processed in groups of 32; inside a group every
+// array is interleaved with the cell index fastest ("lane == cell"), so a warp that
+// walks one matrix row / slot / fine DoF for its 32 cells issues fully coalesced
+// 256-byte accesses:
+//     vals [group][slot          ][32]      per-cell matrix values on the SHARED pattern
+//     coef [group][fine cell][q*7+c][32]    sampled coefficients (sym. tensor 6 + scalar 1)
+//     vec  [group][row][rhs      ][32]      Krylov vectors, all k right-hand sides together
+// Pattern / column indices / assembly tables are shared by all cells and warp-uniform.
+//
+// Kernels (reference lines they replace, paths relative to /root/reference):
+//   k_sample_coefficients  eqn_coeff_A.cc:162-242, eqn_coeff_B.cc:72-91, eqn_rhs.cc:90-107
+//   k_assemble_slots       *_basis.cc assemble_system (ned_rt_basis.cc:362-576): gather form,
+//                          every matrix value written exactly once, no atomics
+//   k_build_precond        (Jacobi / Schur-Jacobi diagonal; replaces SparseILU setup :672-677)
+//   k_lift_rhs             constraints.condense (:1343-1371): b = f_I - A_IB g_B for all k rhs
+//   k_minres_*             solve_iterative (:637-847) + linear_algebra/*.tpp, all k rhs of all
+//                          cells at once, scalars and convergence flags stay on the device
+//   k_finalize_basis       constraints.distribute (:780-838) + set_u_to_std (rt_dq_basis.cc:1039)
+//   k_apply_full, k_gram   assemble_global_element_matrix (:850-948)
+//   k_combine              set_global_weights (:1156-1181)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+#include "engine.h"
+
+namespace msfec {
+
+#define CUDA_OK(call)                                                                               \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess)                                                                          \
+      throw std::runtime_error(std::string(#call) + ": " + cudaGetErrorString(e_));                 \
+  } while (0)
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// Four N(0,1) variates of the harness-defined rough field; must match
+// oracle/msfec_oracle.py:random_field_normals bit-for-bit in the integer part.
+__device__ __forceinline__ void field_normals(unsigned long long seed, unsigned long long gidx, double out[4]) {
+  const unsigned long long base = (gidx * 4ull) ^ (seed * 0xD1342543DE82EF95ull);
+  double f[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    f[c] = ((double)(splitmix64(base + c) >> 11) + 1.0) * (1.0 / 9007199254740992.0);
+  const double r0 = sqrt(-2.0 * log(f[0])), r1 = sqrt(-2.0 * log(f[2]));
+  const double t0 = 2.0 * M_PI * f[1], t1 = 2.0 * M_PI * f[3];
+  out[0] = r0 * cos(t0); out[1] = r0 * sin(t0); out[2] = r1 * cos(t1); out[3] = r1 * sin(t1);
+}
+
+// ------------------------------------------------------------------------------------
+// K1a: coefficient sampling at the physical Gauss points
+// grid (nC, groups), block (32 lanes, 8 q-points)
+// ------------------------------------------------------------------------------------
+__global__ void k_sample_coefficients(CoefParams P, const ExprInstr *__restrict__ prog,
+                                      const double *__restrict__ x0,        // [g][3][32]
+                                      const long long *__restrict__ gid,    // [g][32]
+                                      double h, double *__restrict__ coef,  // [g][nC][56][32]
+                                      double *__restrict__ fr) {            // [g][nC][8*ncomp][32]
+  const int lane = threadIdx.x, q = threadIdx.y, T = blockIdx.x, g = blockIdx.y;
+  const int n = P.n;
+  const int ci = T % n, cj = (T / n) % n, ck = T / (n * n);
+  const double gq[2] = {0.5 - 0.5 / sqrt(3.0), 0.5 + 0.5 / sqrt(3.0)};
+  const double px = x0[(g * 3 + 0) * kLanes + lane] + h * (ci + gq[q & 1]);
+  const double py = x0[(g * 3 + 1) * kLanes + lane] + h * (cj + gq[(q >> 1) & 1]);
+  const double pz = x0[(g * 3 + 2) * kLanes + lane] + h * (ck + gq[q >> 2]);
+  double d[3], s;
+  if (P.use_random) {
+    double xi[4];
+    field_normals(P.seed, (unsigned long long)gid[g * kLanes + lane] * (unsigned long long)P.nC + T, xi);
+    d[0] = exp(P.sigma * xi[0]); d[1] = exp(P.sigma * xi[1]); d[2] = exp(P.sigma * xi[2]);
+    s = exp(P.sigma * xi[3]);
+  } else {
+    d[0] = P.a_scale[0] * (1.0 - P.a_alpha[0] * sin(2.0 * M_PI * P.a_freq[0] * px));
+    d[1] = P.a_scale[1] * (1.0 - P.a_alpha[1] * sin(2.0 * M_PI * P.a_freq[1] * py));
+    d[2] = P.a_scale[2] * (1.0 - P.a_alpha[2] * sin(2.0 * M_PI * P.a_freq[2] * pz));
+    s = expr_eval(prog + P.b_prog_off, P.b_prog_len, px, py, pz);
+  }
+  if (P.tensor_inverse) { d[0] = 1.0 / d[0]; d[1] = 1.0 / d[1]; d[2] = 1.0 / d[2]; }
+  if (P.scalar_inverse) s = 1.0 / s;
+  double *o = coef + ((size_t)(g * P.nC + T) * 56 + q * 7) * kLanes + lane;
+  int c = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+#pragma unroll
+    for (int b = a; b < 3; ++b) {
+      o[(c++) * kLanes] = P.rot[a * 3 + 0] * d[0] * P.rot[b * 3 + 0] + P.rot[a * 3 + 1] * d[1] * P.rot[b * 3 + 1] +
+                          P.rot[a * 3 + 2] * d[2] * P.rot[b * 3 + 2];
+    }
+  o[6 * kLanes] = s;
+  for (int cc = 0; cc < P.rhs_ncomp; ++cc)
+    fr[((size_t)(g * P.nC + T) * (8 * P.rhs_ncomp) + q * P.rhs_ncomp + cc) * kLanes + lane] =
+        expr_eval(prog + P.rhs_prog_off[cc], P.rhs_prog_len[cc], px, py, pz);
+}
+
+// ------------------------------------------------------------------------------------
+// K1b: gather assembly into slots.  grid (ceil(n_slots/8), groups), block (32, 8)
+// ------------------------------------------------------------------------------------
+struct AsmDev {
+  int n_slots, coef_stride;
+  const int *contrib_ptr, *contrib_cell, *contrib_pair, *pair_ptr, *pair_idx;
+  const double *pair_w;
+};
+
+__global__ void k_assemble_slots(AsmDev A, int nC, const double *__restrict__ coef, double scale,
+                                 double *__restrict__ out, int out_stride, int out_off) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int slot = blockIdx.x * blockDim.y + threadIdx.y;
+  if (slot >= A.n_slots) return;
+  double acc = 0.0;
+  for (int c = A.contrib_ptr[slot]; c < A.contrib_ptr[slot + 1]; ++c) {
+    const double *cf = coef + ((size_t)(g * nC + A.contrib_cell[c]) * A.coef_stride) * kLanes + lane;
+    const int p = A.contrib_pair[c];
+    for (int e = A.pair_ptr[p]; e < A.pair_ptr[p + 1]; ++e) acc = fma(A.pair_w[e], cf[(size_t)A.pair_idx[e] * kLanes], acc);
+  }
+  out[((size_t)g * out_stride + out_off + slot) * kLanes + lane] = acc * scale;
+}
+
+// ------------------------------------------------------------------------------------
+// operator in device memory
+// ------------------------------------------------------------------------------------
+struct OpDev {
+  int n_rows;
+  const int *cptr, *ccol, *cref, *sptr, *scol;
+  const double *sval;
+};
+
+// Jacobi diagonal of the symmetric-form system: block 0 -> diag(A00); block 1 ->
+// diag(K diag(A00)^-1 K^T + A11).   grid (ceil(NI/8), groups), block (32, 8)
+__global__ void k_build_precond(int NI0, int NI, int n_slots, const int *__restrict__ diag0,
+                                const int *__restrict__ diag1, OpDev kint, double kscale,
+                                const double *__restrict__ vals, double *__restrict__ minv) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= NI) return;
+  const double *v = vals + (size_t)g * n_slots * kLanes + lane;
+  double d;
+  if (row < NI0) {
+    d = v[(size_t)diag0[row] * kLanes];
+  } else {
+    const int r = row - NI0;
+    d = diag1[r] >= 0 ? v[(size_t)diag1[r] * kLanes] : 0.0;
+    for (int e = kint.sptr[r]; e < kint.sptr[r + 1]; ++e) {
+      const double kv = kint.sval[e] * kscale;
+      d += kv * kv / v[(size_t)diag0[kint.scol[e]] * kLanes];
+    }
+  }
+  minv[((size_t)g * NI + row) * kLanes + lane] = 1.0 / d;
+}
+
+constexpr int kMaxK = 20;
+
+// b = F1 * f1scale + Lift * G  for all k right-hand sides.  grid (ceil(NI/4), groups), block (32, 4)
+__global__ void k_lift_rhs(OpDev L, int NI, int NB, int k, int n_slots, double kscale, double f1scale,
+                           const double *__restrict__ vals, const double *__restrict__ G,
+                           const double *__restrict__ F1, double *__restrict__ b) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= NI) return;
+  const double *v = vals + (size_t)g * n_slots * kLanes + lane;
+  double acc[kMaxK];
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) acc[j] = j < k ? F1[(size_t)j * NI + row] * f1scale : 0.0;
+  for (int e = L.cptr[row]; e < L.cptr[row + 1]; ++e) {
+    const int ref = L.cref[e], col = L.ccol[e];
+    double a = v[(size_t)(ref >> 1) * kLanes];
+    if (ref & 1) a = -a;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < k) acc[j] = fma(a, G[(size_t)j * NB + col], acc[j]);
+  }
+  for (int e = L.sptr[row]; e < L.sptr[row + 1]; ++e) {
+    const double a = L.sval[e] * kscale;
+    const int col = L.scol[e];
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < k) acc[j] = fma(a, G[(size_t)j * NB + col], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) if (j < k) b[(((size_t)g * NI + row) * k + j) * kLanes + lane] = acc[j];
+}
+
+// ------------------------------------------------------------------------------------
+// MINRES (Paige-Saunders, diagonal preconditioner), all k rhs of all cells at once.
+// Per-(cell, rhs) scalars live in sc[field][g][k][32].
+// ------------------------------------------------------------------------------------
+enum ScalarField {
+  S_BETA = 0, S_OLDB, S_DBAR, S_EPSLN, S_PHIBAR, S_CS, S_SN, S_BETA1, S_ALFA_ACC, S_BSQ_ACC,
+  S_COEF_S, S_COEF_C1, S_OLDEPS, S_DELTA, S_GINV, S_PHI, S_ACTIVE, S_ITERS, S_NFIELDS
+};
+
+struct MinresDev {
+  int NI, k, n_slots;
+  size_t sc_stride;   // groups * k * 32
+  double *sc;
+};
+
+__device__ __forceinline__ double &SC(const MinresDev &M, int f, int g, int j, int lane) {
+  return M.sc[(size_t)f * M.sc_stride + ((size_t)g * M.k + j) * kLanes + lane];
+}
+
+constexpr int kRW = 4;            // rows in flight per block (threadIdx.z)
+constexpr int kRowsPerBlock = 32; // rows handled by one block
+
+// Kernel A:  v = s*yp ;  T = Sys v - c1 r1 ;  alfa += v.T
+// grid (ceil(NI/kRowsPerBlock), groups), block (32, k/R, kRW)
+template <int R>
+__global__ void __launch_bounds__(32 * 5 * kRW)
+k_minres_spmm(MinresDev M, OpDev S, double kscale, const double *__restrict__ vals,
+              const double *__restrict__ yp, const double *__restrict__ r1,
+              double *__restrict__ V, double *__restrict__ T) {
+  __shared__ double red[kRW][kMaxK][kLanes];
+  const int lane = threadIdx.x, ch = threadIdx.y, rw = threadIdx.z, g = blockIdx.y;
+  const int j0 = ch * R, k = M.k, NI = M.NI;
+  double s[R], c1[R], alfa[R];
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    s[jj] = SC(M, S_COEF_S, g, j0 + jj, lane);
+    c1[jj] = SC(M, S_COEF_C1, g, j0 + jj, lane);
+    alfa[jj] = 0.0;
+  }
+  const double *v = vals + (size_t)g * M.n_slots * kLanes + lane;
+  const double *ypg = yp + ((size_t)g * NI * k + j0) * kLanes + lane;
+  const int row_end = min(NI, (int)(blockIdx.x + 1) * kRowsPerBlock);
+  for (int row = blockIdx.x * kRowsPerBlock + rw; row < row_end; row += kRW) {
+    double sum[R];
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) sum[jj] = 0.0;
+    for (int e = S.cptr[row]; e < S.cptr[row + 1]; ++e) {
+      const int ref = S.cref[e];
+      double a = v[(size_t)(ref >> 1) * kLanes];
+      if (ref & 1) a = -a;
+      const double *x = ypg + (size_t)S.ccol[e] * k * kLanes;
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) sum[jj] = fma(a, x[jj * kLanes], sum[jj]);
+    }
+    for (int e = S.sptr[row]; e < S.sptr[row + 1]; ++e) {
+      const double a = S.sval[e] * kscale;
+      const double *x = ypg + (size_t)S.scol[e] * k * kLanes;
+#pragma unroll
+      for (int jj = 0; jj < R; ++jj) sum[jj] = fma(a, x[jj * kLanes], sum[jj]);
+    }
+    const size_t o = (((size_t)g * NI + row) * k + j0) * kLanes + lane;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const double vv = yp[o + jj * kLanes] * s[jj];
+      const double tt = sum[jj] * s[jj] - c1[jj] * r1[o + jj * kLanes];
+      V[o + jj * kLanes] = vv;
+      T[o + jj * kLanes] = tt;
+      alfa[jj] = fma(vv, tt, alfa[jj]);
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) red[rw][j0 + jj][lane] = alfa[jj];
+  __syncthreads();
+  if (rw == 0) {
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRW; ++w) a += red[w][j0 + jj][lane];
+      atomicAdd(&SC(M, S_ALFA_ACC, g, j0 + jj, lane), a);
+    }
+  }
+}
+
+// Kernel B:  t = T - (alfa/beta) r2 ;  r_new = t ;  yp = Minv t ;  bsq += t.yp
+// Also used for initialisation (init=1): t = b (in T), alfa term skipped.
+template <int R>
+__global__ void __launch_bounds__(32 * 5 * kRW)
+k_minres_update(MinresDev M, int init, const double *__restrict__ minv, const double *__restrict__ T,
+                const double *__restrict__ r2, double *__restrict__ rnew, double *__restrict__ yp) {
+  __shared__ double red[kRW][kMaxK][kLanes];
+  const int lane = threadIdx.x, ch = threadIdx.y, rw = threadIdx.z, g = blockIdx.y;
+  const int j0 = ch * R, k = M.k, NI = M.NI;
+  double cb[R], bsq[R];
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    const double act = SC(M, S_ACTIVE, g, j0 + jj, lane), beta = SC(M, S_BETA, g, j0 + jj, lane);
+    cb[jj] = (!init && act != 0.0 && beta > 0.0) ? SC(M, S_ALFA_ACC, g, j0 + jj, lane) / beta : 0.0;
+    bsq[jj] = 0.0;
+  }
+  const int row_end = min(NI, (int)(blockIdx.x + 1) * kRowsPerBlock);
+  for (int row = blockIdx.x * kRowsPerBlock + rw; row < row_end; row += kRW) {
+    const double mi = minv[((size_t)g * NI + row) * kLanes + lane];
+    const size_t o = (((size_t)g * NI + row) * k + j0) * kLanes + lane;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      double tt = T[o + jj * kLanes];
+      if (!init) tt -= cb[jj] * r2[o + jj * kLanes];
+      const double y = mi * tt;
+      rnew[o + jj * kLanes] = tt;
+      yp[o + jj * kLanes] = y;
+      bsq[jj] = fma(tt, y, bsq[jj]);
+    }
+  }
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) red[rw][j0 + jj][lane] = bsq[jj];
+  __syncthreads();
+  if (rw == 0) {
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      double a = 0.0;
+#pragma unroll
+      for (int w = 0; w < kRW; ++w) a += red[w][j0 + jj][lane];
+      atomicAdd(&SC(M, S_BSQ_ACC, g, j0 + jj, lane), a);
+    }
+  }
+}
+
+// Kernel S: scalar recurrences.  grid (groups), block (32, k)
+__global__ void k_minres_scalars(MinresDev M, int init, double rtol) {
+  const int lane = threadIdx.x, j = threadIdx.y, g = blockIdx.x;
+#define F(f) SC(M, f, g, j, lane)
+  if (init) {
+    const double b1 = sqrt(fmax(F(S_BSQ_ACC), 0.0));
+    F(S_BETA1) = b1; F(S_BETA) = b1; F(S_OLDB) = 0.0; F(S_DBAR) = 0.0; F(S_EPSLN) = 0.0;
+    F(S_PHIBAR) = b1; F(S_CS) = -1.0; F(S_SN) = 0.0;
+    F(S_ACTIVE) = b1 > 0.0 ? 1.0 : 0.0;
+    F(S_COEF_S) = b1 > 0.0 ? 1.0 / b1 : 0.0; F(S_COEF_C1) = 0.0;
+    F(S_OLDEPS) = 0.0; F(S_DELTA) = 0.0; F(S_GINV) = 0.0; F(S_PHI) = 0.0; F(S_ITERS) = 0.0;
+    F(S_ALFA_ACC) = 0.0; F(S_BSQ_ACC) = 0.0;
+    return;
+  }
+  if (F(S_ACTIVE) == 0.0) {
+    F(S_COEF_S) = 0.0; F(S_COEF_C1) = 0.0; F(S_OLDEPS) = 0.0; F(S_DELTA) = 0.0; F(S_GINV) = 0.0; F(S_PHI) = 0.0;
+    F(S_ALFA_ACC) = 0.0; F(S_BSQ_ACC) = 0.0;
+    return;
+  }
+  const double alfa = F(S_ALFA_ACC), oldb = F(S_BETA);
+  const double beta = sqrt(fmax(F(S_BSQ_ACC), 0.0));
+  const double cs = F(S_CS), sn = F(S_SN), dbar = F(S_DBAR);
+  const double oldeps = F(S_EPSLN);
+  const double delta = cs * dbar + sn * alfa;
+  const double gbar = sn * dbar - cs * alfa;
+  const double epsln = sn * beta;
+  const double ndbar = -cs * beta;
+  double gamma = sqrt(gbar * gbar + beta * beta);
+  gamma = fmax(gamma, 1e-300);
+  const double ncs = gbar / gamma, nsn = beta / gamma;
+  const double phibar = F(S_PHIBAR);
+  const double phi = ncs * phibar, nphibar = nsn * phibar;
+  F(S_OLDB) = oldb; F(S_BETA) = beta; F(S_DBAR) = ndbar; F(S_EPSLN) = epsln; F(S_CS) = ncs; F(S_SN) = nsn;
+  F(S_PHIBAR) = nphibar;
+  F(S_OLDEPS) = oldeps; F(S_DELTA) = delta; F(S_GINV) = 1.0 / gamma; F(S_PHI) = phi;
+  F(S_ITERS) += 1.0;
+  const bool done = !(fabs(nphibar) > rtol * F(S_BETA1)) || !(beta > 0.0);
+  F(S_ACTIVE) = done ? 0.0 : 1.0;
+  F(S_COEF_S) = done ? 0.0 : 1.0 / beta;
+  F(S_COEF_C1) = done ? 0.0 : beta / oldb;
+  F(S_ALFA_ACC) = 0.0; F(S_BSQ_ACC) = 0.0;
+#undef F
+}
+
+// Kernel W:  w_new = (v - oldeps w1 - delta w2) / gamma  (stored over w1) ;  x += phi w_new
+// grid (ceil(NI/kRowsPerBlock), groups), block (32, k/R, kRW)
+template <int R>
+__global__ void __launch_bounds__(32 * 5 * kRW)
+k_minres_wx(MinresDev M, const double *__restrict__ V, double *__restrict__ w1, const double *__restrict__ w2,
+            double *__restrict__ x) {
+  const int lane = threadIdx.x, ch = threadIdx.y, rw = threadIdx.z, g = blockIdx.y;
+  const int j0 = ch * R, k = M.k, NI = M.NI;
+  double oe[R], de[R], gi[R], ph[R];
+#pragma unroll
+  for (int jj = 0; jj < R; ++jj) {
+    oe[jj] = SC(M, S_OLDEPS, g, j0 + jj, lane); de[jj] = SC(M, S_DELTA, g, j0 + jj, lane);
+    gi[jj] = SC(M, S_GINV, g, j0 + jj, lane); ph[jj] = SC(M, S_PHI, g, j0 + jj, lane);
+  }
+  const int row_end = min(NI, (int)(blockIdx.x + 1) * kRowsPerBlock);
+  for (int row = blockIdx.x * kRowsPerBlock + rw; row < row_end; row += kRW) {
+    const size_t o = (((size_t)g * NI + row) * k + j0) * kLanes + lane;
+#pragma unroll
+    for (int jj = 0; jj < R; ++jj) {
+      const size_t i = o + jj * kLanes;
+      const double wn = (V[i] - oe[jj] * w1[i] - de[jj] * w2[i]) * gi[jj];
+      w1[i] = wn;
+      x[i] = fma(ph[jj], wn, x[i]);
+    }
+  }
+}
+
+// number of still-active columns (cells beyond n_valid are ignored)
+__global__ void k_count_active(MinresDev M, int groups, int n_valid, int *out) {
+  const int lane = threadIdx.x, j = threadIdx.y, g = blockIdx.x;
+  if (g * kLanes + lane >= n_valid) return;
+  if (SC(M, S_ACTIVE, g, j, lane) != 0.0) atomicAdd(out, 1);
+}
+
+// ------------------------------------------------------------------------------------
+// Basis store Z[gz][full dof][kg][32], Gram
+// ------------------------------------------------------------------------------------
+struct BasisDims { int NI0, NI1, N0, N1, NB0, NI, NB, NF, k, kg, k0, one_u; };
+
+// grid (ceil(NF/8), groups), block (32, 8)
+__global__ void k_finalize_basis(BasisDims D, const double *__restrict__ x, const double *__restrict__ G,
+                                 double *__restrict__ Z, int gz0) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int d = blockIdx.x * blockDim.y + threadIdx.y;
+  if (d >= D.NF) return;
+  double *z = Z + (((size_t)(gz0 + g) * D.NF + d) * D.kg) * kLanes + lane;
+  for (int j = 0; j < D.kg; ++j) {
+    double val = 0.0;
+    if (d < D.N0) {
+      if (j < D.k0) val = d < D.NI0 ? x[(((size_t)g * D.NI + d) * D.k + j) * kLanes + lane] : G[(size_t)j * D.NB + d - D.NI0];
+    } else {
+      const int d1 = d - D.N0;
+      if (j >= D.k0) {
+        if (D.one_u) val = 1.0;   // RT_DQ: u := 1 (rt_dq_basis.cc:1039-1043)
+        else val = d1 < D.NI1 ? x[(((size_t)g * D.NI + D.NI0 + d1) * D.k + j) * kLanes + lane]
+                               : G[(size_t)j * D.NB + D.NB0 + d1 - D.NI1];
+      }
+    }
+    z[(size_t)j * kLanes] = val;
+  }
+}
+
+// Y = Full * Z.  grid (ceil(NF/4), groups), block (32, 4)
+__global__ void k_apply_full(OpDev A, int NF, int kg, int n_slots, double kscale, const double *__restrict__ vals,
+                             const double *__restrict__ Z, int gz0, double *__restrict__ Y) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= NF) return;
+  const double *v = vals + (size_t)g * n_slots * kLanes + lane;
+  const double *zg = Z + ((size_t)(gz0 + g) * NF * kg) * kLanes + lane;
+  double acc[kMaxK];
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) acc[j] = 0.0;
+  for (int e = A.cptr[row]; e < A.cptr[row + 1]; ++e) {
+    const int ref = A.cref[e];
+    double a = v[(size_t)(ref >> 1) * kLanes];
+    if (ref & 1) a = -a;
+    const double *z = zg + (size_t)A.ccol[e] * kg * kLanes;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < kg) acc[j] = fma(a, z[j * kLanes], acc[j]);
+  }
+  for (int e = A.sptr[row]; e < A.sptr[row + 1]; ++e) {
+    const double a = A.sval[e] * kscale;
+    const double *z = zg + (size_t)A.scol[e] * kg * kLanes;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < kg) acc[j] = fma(a, z[j * kLanes], acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) if (j < kg) Y[(((size_t)g * NF + row) * kg + j) * kLanes + lane] = acc[j];
+}
+
+// M[cell][i][j] = sum_d Z[d][i] Y[d][j] ;  r[cell][i] = sum_{d in rhs block} Z[d][i] grhs[d]
+// grid (kg, groups), block (32, kg)
+__global__ void k_gram(int NF, int kg, const double *__restrict__ Z, int gz0, const double *__restrict__ Y,
+                       const double *__restrict__ grhs, int rhs_off, int n_rhs, int cell0, int n_cells,
+                       double *__restrict__ Mout, double *__restrict__ rout) {
+  const int lane = threadIdx.x, j = threadIdx.y, i = blockIdx.x, g = blockIdx.y;
+  const double *z = Z + (((size_t)(gz0 + g) * NF) * kg + i) * kLanes + lane;
+  const double *y = Y + (((size_t)g * NF) * kg + j) * kLanes + lane;
+  double acc = 0.0;
+  for (int d = 0; d < NF; ++d) acc = fma(z[(size_t)d * kg * kLanes], y[(size_t)d * kg * kLanes], acc);
+  const int cell = cell0 + g * kLanes + lane;
+  if (cell < n_cells) Mout[((size_t)cell * kg + i) * kg + j] = acc;
+  if (j == 0) {
+    double r = 0.0;
+    for (int d = 0; d < n_rhs; ++d)
+      r = fma(z[(size_t)(rhs_off + d) * kg * kLanes], grhs[((size_t)g * n_rhs + d) * kLanes + lane], r);
+    if (cell < n_cells) rout[(size_t)cell * kg + i] = r;
+  }
+}
+
+// u_fine[gz][d][32] = sum_j w[cell][j] Z[gz][d][j][32]    grid (ceil(NF/8), groups_all), block (32, 8)
+__global__ void k_combine(int NF, int kg, int n_cells, const double *__restrict__ Z, const double *__restrict__ wts,
+                          double *__restrict__ U) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int d = blockIdx.x * blockDim.y + threadIdx.y;
+  if (d >= NF) return;
+  const int cell = min(g * kLanes + lane, n_cells - 1);
+  const double *z = Z + (((size_t)g * NF + d) * kg) * kLanes + lane;
+  double acc = 0.0;
+  for (int j = 0; j < kg; ++j) acc = fma(wts[(size_t)cell * kg + j], z[(size_t)j * kLanes], acc);
+  U[((size_t)g * NF + d) * kLanes + lane] = acc;
+}
+
+// Validate corners (axis-aligned cubes of edge H) and scatter origins into the interleaved
+// layout.  One thread per cell of the batch; lanes beyond n_cells replicate the last cell.
+__global__ void k_prepare_cells(const double *__restrict__ corners, const long long *__restrict__ ids, int cell0,
+                                int n_batch, int n_total, double H, double *__restrict__ x0,
+                                long long *__restrict__ gid, int *__restrict__ bad) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int groups = (n_batch + kLanes - 1) / kLanes;
+  if (t >= groups * kLanes) return;
+  const int cell = cell0 + min(t, n_batch - 1);
+  const double *c = corners + (size_t)cell * 24;
+  const double tol = 1e-12 * fmax(1.0, fabs(H));
+  for (int v = 0; v < 8; ++v) {
+    const double ex = c[0] + ((v & 1) ? H : 0.0), ey = c[1] + (((v >> 1) & 1) ? H : 0.0), ez = c[2] + ((v >> 2) ? H : 0.0);
+    if (fabs(c[3 * v] - ex) > tol || fabs(c[3 * v + 1] - ey) > tol || fabs(c[3 * v + 2] - ez) > tol) atomicExch(bad, 1 + cell);
+  }
+  const int g = t / kLanes, lane = t % kLanes;
+  for (int d = 0; d < 3; ++d) x0[(g * 3 + d) * kLanes + lane] = c[d];
+  gid[g * kLanes + lane] = ids ? ids[cell] : (long long)cell;
+}
+
+template <typename T>
+T *dev_upload(const std::vector<T> &h) {
+  T *d = nullptr;
+  CUDA_OK(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+  if (!h.empty()) CUDA_OK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return d;
+}
+
+struct OpStore {
+  int *cptr = nullptr, *ccol = nullptr, *cref = nullptr, *sptr = nullptr, *scol = nullptr;
+  double *sval = nullptr;
+  OpDev dev{};
+  void upload(const RefOperator &o) {
+    cptr = dev_upload(o.cptr); ccol = dev_upload(o.ccol); cref = dev_upload(o.cref);
+    sptr = dev_upload(o.sptr); scol = dev_upload(o.scol); sval = dev_upload(o.sval);
+    dev = {o.n_rows, cptr, ccol, cref, sptr, scol, sval};
+  }
+  void release() {
+    cudaFree(cptr); cudaFree(ccol); cudaFree(cref); cudaFree(sptr); cudaFree(scol); cudaFree(sval);
+  }
+};
+
+struct AsmStore {
+  int *contrib_ptr = nullptr, *contrib_cell = nullptr, *contrib_pair = nullptr, *pair_ptr = nullptr, *pair_idx = nullptr;
+  double *pair_w = nullptr;
+  AsmDev dev{};
+  void upload(const AsmTable &t) {
+    contrib_ptr = dev_upload(t.contrib_ptr); contrib_cell = dev_upload(t.contrib_cell);
+    contrib_pair = dev_upload(t.contrib_pair); pair_ptr = dev_upload(t.pair_ptr);
+    pair_idx = dev_upload(t.pair_idx); pair_w = dev_upload(t.pair_w);
+    dev = {t.n_slots, t.coef_stride, contrib_ptr, contrib_cell, contrib_pair, pair_ptr, pair_idx, pair_w};
+  }
+  void release() {
+    cudaFree(contrib_ptr); cudaFree(contrib_cell); cudaFree(contrib_pair); cudaFree(pair_ptr); cudaFree(pair_idx);
+    cudaFree(pair_w);
+  }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------
+class Engine {
+ public:
+  Engine(int device, const ProblemSpec &spec, const Topology &topo) : spec_(spec), T_(topo), device_(device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) throw std::runtime_error("no CUDA device available (there is no CPU fallback)");
+    if (device >= count) throw std::runtime_error("CUDA device index out of range");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) throw std::runtime_error(std::string("device '") + prop.name + "' is not sm_100 class");
+    CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+    for (auto &ev : ev_) CUDA_OK(cudaEventCreate(&ev));
+    for (auto &ev : ev_sp_) CUDA_OK(cudaEventCreate(&ev));
+    sys_.upload(T_.sys); lift_.upload(T_.lift); full_.upload(T_.full); kint_.upload(T_.kint);
+    asm00_.upload(T_.asm00); asm11_.upload(T_.asm11); asmrhs_.upload(T_.asm_rhs);
+    d_diag0_ = dev_upload(T_.diag_slot0); d_diag1_ = dev_upload(T_.diag_slot1);
+    d_G_ = dev_upload(T_.G); d_F1_ = dev_upload(T_.F1);
+    d_prog_ = dev_upload(spec_.programs);
+    CUDA_OK(cudaMalloc(&d_flag_, 2 * sizeof(int)));
+    CUDA_OK(cudaMallocHost(&h_flag_, 2 * sizeof(int)));
+    n_slots_ = T_.n_slots0 + T_.n_slots1;
+    R_ = (T_.k_solve % 6 == 0) ? 6 : 4;
+    if (T_.k_solve % R_) throw std::runtime_error("unsupported number of right-hand sides");
+  }
+
+  ~Engine() {
+    cudaSetDevice(device_);
+    free_batch(); free_store();
+    sys_.release(); lift_.release(); full_.release(); kint_.release();
+    asm00_.release(); asm11_.release(); asmrhs_.release();
+    cudaFree(d_diag0_); cudaFree(d_diag1_); cudaFree(d_G_); cudaFree(d_F1_); cudaFree(d_prog_);
+    cudaFree(d_flag_); cudaFreeHost(h_flag_);
+    for (auto &ev : ev_) cudaEventDestroy(ev);
+    for (auto &ev : ev_sp_) cudaEventDestroy(ev);
+    cudaStreamDestroy(stream_);
+  }
+
+  int build(int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix, double *elem_rhs,
+            bool device_ptrs, msfec_stats *stats);
+  void set_weights(int n_cells, const double *weights);
+  void get_fine_solution(int cell, double *b0, double *b1);
+  void get_basis(int cell, int basis, double *b0, double *b1);
+  void cell_values(int cell, double *values, size_t *count);
+
+ private:
+  void alloc_batch(int groups);
+  void free_batch();
+  void alloc_store(int n_cells);
+  void free_store();
+  int solve_batch(int groups, int n_valid, double kscale, msfec_stats &st, double &ms_spmm);
+  template <int R> void launch_iteration(int groups, double kscale, int parity, double rtol, bool time_spmm);
+  template <int R> void launch_init(int groups, double rtol);
+
+  ProblemSpec spec_;
+  Topology T_;
+  int device_;
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev_[8]{}, ev_sp_[2]{};
+  long spmm_samples_ = 0;
+  double cell_iters_ = 0;
+  OpStore sys_, lift_, full_, kint_;
+  AsmStore asm00_, asm11_, asmrhs_;
+  int *d_diag0_ = nullptr, *d_diag1_ = nullptr;
+  double *d_G_ = nullptr, *d_F1_ = nullptr;
+  ExprInstr *d_prog_ = nullptr;
+  int *d_flag_ = nullptr, *h_flag_ = nullptr;
+  int n_slots_ = 0, R_ = 4;
+  // batch buffers
+  int batch_groups_ = 0;
+  double *d_x0_ = nullptr, *d_coef_ = nullptr, *d_fr_ = nullptr, *d_vals_ = nullptr, *d_grhs_ = nullptr, *d_minv_ = nullptr;
+  long long *d_gid_ = nullptr;
+  double *d_vec_[8]{};   // ra, rb, T, yp, V, wa, wb, x
+  double *d_sc_ = nullptr, *d_Y_ = nullptr;
+  // store for all cells of the last build
+  int store_cells_ = 0, store_groups_ = 0;
+  double *d_Z_ = nullptr, *d_U_ = nullptr, *d_M_ = nullptr, *d_r_ = nullptr, *d_corners_ = nullptr, *d_w_ = nullptr;
+  long long *d_ids_ = nullptr;
+  bool have_weights_ = false;
+  int last_batch_cell0_ = 0, last_batch_n_ = 0;
+  long launches_ = 0;
+};
+
+void Engine::free_batch() {
+  cudaFree(d_x0_); cudaFree(d_coef_); cudaFree(d_fr_); cudaFree(d_vals_); cudaFree(d_grhs_); cudaFree(d_minv_);
+  cudaFree(d_gid_); cudaFree(d_sc_); cudaFree(d_Y_);
+  for (auto &p : d_vec_) { cudaFree(p); p = nullptr; }
+  d_x0_ = d_coef_ = d_fr_ = d_vals_ = d_grhs_ = d_minv_ = d_sc_ = d_Y_ = nullptr; d_gid_ = nullptr;
+  batch_groups_ = 0;
+}
+
+void Engine::alloc_batch(int groups) {
+  if (groups <= batch_groups_) return;
+  free_batch();
+  const size_t G = groups, L = kLanes * sizeof(double);
+  CUDA_OK(cudaMalloc(&d_x0_, G * 3 * L));
+  CUDA_OK(cudaMalloc(&d_gid_, G * kLanes * sizeof(long long)));
+  CUDA_OK(cudaMalloc(&d_coef_, G * T_.nC * 56 * L));
+  CUDA_OK(cudaMalloc(&d_fr_, G * T_.nC * 8 * T_.rhs_ncomp * L));
+  CUDA_OK(cudaMalloc(&d_vals_, G * std::max(n_slots_, 1) * L));
+  CUDA_OK(cudaMalloc(&d_grhs_, G * T_.asm_rhs.n_slots * L));
+  CUDA_OK(cudaMalloc(&d_minv_, G * T_.NI * L));
+  for (auto &p : d_vec_) CUDA_OK(cudaMalloc(&p, G * T_.NI * T_.k_solve * L));
+  CUDA_OK(cudaMalloc(&d_sc_, (size_t)S_NFIELDS * G * T_.k_solve * L));
+  CUDA_OK(cudaMalloc(&d_Y_, G * T_.NF * T_.k_gram * L));
+  batch_groups_ = groups;
+}
+
+void Engine::free_store() {
+  cudaFree(d_Z_); cudaFree(d_U_); cudaFree(d_M_); cudaFree(d_r_); cudaFree(d_corners_); cudaFree(d_ids_); cudaFree(d_w_);
+  d_Z_ = d_U_ = d_M_ = d_r_ = d_corners_ = d_w_ = nullptr; d_ids_ = nullptr;
+  store_cells_ = store_groups_ = 0;
+}
+
+void Engine::alloc_store(int n_cells) {
+  const int groups = (n_cells + kLanes - 1) / kLanes;
+  if (n_cells <= store_cells_ && groups <= store_groups_) return;
+  free_store();
+  const size_t L = kLanes * sizeof(double);
+  CUDA_OK(cudaMalloc(&d_Z_, (size_t)groups * T_.NF * T_.k_gram * L));
+  CUDA_OK(cudaMalloc(&d_M_, (size_t)n_cells * T_.k_gram * T_.k_gram * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_r_, (size_t)n_cells * T_.k_gram * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_corners_, (size_t)n_cells * 24 * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_ids_, (size_t)n_cells * sizeof(long long)));
+  store_cells_ = n_cells; store_groups_ = groups;
+}
+
+template <int R>
+void Engine::launch_init(int groups, double rtol) {
+  MinresDev M{T_.NI, T_.k_solve, n_slots_, (size_t)groups * T_.k_solve * kLanes, d_sc_};
+  const dim3 blk(kLanes, T_.k_solve / R, kRW), grd((T_.NI + kRowsPerBlock - 1) / kRowsPerBlock, groups);
+  // b was written into T (d_vec_[2]); r2 := b goes to rb (d_vec_[1]); yp = Minv b
+  k_minres_update<R><<<grd, blk, 0, stream_>>>(M, 1, d_minv_, d_vec_[2], d_vec_[0], d_vec_[1], d_vec_[3]);
+  k_minres_scalars<<<groups, dim3(kLanes, T_.k_solve), 0, stream_>>>(M, 1, rtol);
+  launches_ += 2;
+}
+
+template <int R>
+void Engine::launch_iteration(int groups, double kscale, int parity, double rtol, bool time_spmm) {
+  MinresDev M{T_.NI, T_.k_solve, n_slots_, (size_t)groups * T_.k_solve * kLanes, d_sc_};
+  const dim3 blk(kLanes, T_.k_solve / R, kRW), grd((T_.NI + kRowsPerBlock - 1) / kRowsPerBlock, groups);
+  double *r1 = d_vec_[parity ? 1 : 0], *r2 = d_vec_[parity ? 0 : 1];
+  double *w1 = d_vec_[parity ? 6 : 5], *w2 = d_vec_[parity ? 5 : 6];
+  if (time_spmm) CUDA_OK(cudaEventRecord(ev_sp_[0], stream_));
+  k_minres_spmm<R><<<grd, blk, 0, stream_>>>(M, sys_.dev, kscale, d_vals_, d_vec_[3], r1, d_vec_[4], d_vec_[2]);
+  if (time_spmm) CUDA_OK(cudaEventRecord(ev_sp_[1], stream_));
+  k_minres_update<R><<<grd, blk, 0, stream_>>>(M, 0, d_minv_, d_vec_[2], r2, r1, d_vec_[3]);
+  k_minres_scalars<<<groups, dim3(kLanes, T_.k_solve), 0, stream_>>>(M, 0, rtol);
+  k_minres_wx<R><<<grd, blk, 0, stream_>>>(M, d_vec_[4], w1, w2, d_vec_[7]);
+  launches_ += 4;
+}
+
+int Engine::solve_batch(int groups, int n_valid, double kscale, msfec_stats &st, double &ms_spmm) {
+  const double rtol = spec_.p.krylov_rtol > 0 ? spec_.p.krylov_rtol : 1e-13;
+  const int max_iter = spec_.p.krylov_max_iter > 0 ? spec_.p.krylov_max_iter : 20 * T_.NI;
+  const size_t vec_bytes = (size_t)groups * T_.NI * T_.k_solve * kLanes * sizeof(double);
+  // ra (r1) must be finite: it is multiplied by c1 = 0 in the first iteration
+  for (int i : {0, 4, 5, 6, 7}) CUDA_OK(cudaMemsetAsync(d_vec_[i], 0, vec_bytes, stream_));
+  CUDA_OK(cudaMemsetAsync(d_sc_, 0, (size_t)S_NFIELDS * groups * T_.k_solve * kLanes * sizeof(double), stream_));
+  if (R_ == 6) launch_init<6>(groups, rtol); else launch_init<4>(groups, rtol);
+  MinresDev M{T_.NI, T_.k_solve, n_slots_, (size_t)groups * T_.k_solve * kLanes, d_sc_};
+  const int check_every = 16;
+  int it = 0, active = 1;
+  while (it < max_iter && active > 0) {
+    for (int c = 0; c < check_every; ++c, ++it) {
+      if (R_ == 6) launch_iteration<6>(groups, kscale, it & 1, rtol, c == 0);
+      else launch_iteration<4>(groups, kscale, it & 1, rtol, c == 0);
+    }
+    CUDA_OK(cudaMemsetAsync(d_flag_, 0, sizeof(int), stream_));
+    k_count_active<<<groups, dim3(kLanes, T_.k_solve), 0, stream_>>>(M, groups, n_valid, d_flag_);
+    ++launches_;
+    CUDA_OK(cudaMemcpyAsync(h_flag_, d_flag_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    active = h_flag_[0];
+    float ms = 0;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev_sp_[0], ev_sp_[1]));
+    ms_spmm += ms; ++spmm_samples_;
+  }
+  // statistics
+  std::vector<double> iters((size_t)groups * T_.k_solve * kLanes), phib(iters.size()), beta1(iters.size());
+  const size_t fs = iters.size() * sizeof(double);
+  CUDA_OK(cudaMemcpy(iters.data(), d_sc_ + (size_t)S_ITERS * iters.size(), fs, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(phib.data(), d_sc_ + (size_t)S_PHIBAR * iters.size(), fs, cudaMemcpyDeviceToHost));
+  CUDA_OK(cudaMemcpy(beta1.data(), d_sc_ + (size_t)S_BETA1 * iters.size(), fs, cudaMemcpyDeviceToHost));
+  double sum = 0;
+  long cnt = 0;
+  for (int g = 0; g < groups; ++g) for (int j = 0; j < T_.k_solve; ++j) for (int l = 0; l < kLanes; ++l) {
+    if (g * kLanes + l >= n_valid) continue;
+    const size_t i = ((size_t)g * T_.k_solve + j) * kLanes + l;
+    st.iterations_max = std::max(st.iterations_max, (int)iters[i]);
+    sum += iters[i]; ++cnt;
+    const double rel = beta1[i] > 0 ? std::fabs(phib[i]) / beta1[i] : 0.0;
+    st.residual_max = std::max(st.residual_max, rel);
+    if (!(rel <= rtol)) st.not_converged++;
+  }
+  st.iterations_mean += sum;   // normalised by the caller
+  return it;
+}
+
+int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix, double *elem_rhs,
+                  bool device_ptrs, msfec_stats *stats) {
+  CUDA_OK(cudaSetDevice(device_));
+  if (n_cells <= 0) throw std::invalid_argument("n_cells must be positive");
+  msfec_stats st{};
+  st.n_cells = n_cells; st.k = T_.k_gram; st.n_fine_dofs = T_.NF; st.n_fine_dofs_interior = T_.NI;
+  launches_ = 0; spmm_samples_ = 0; cell_iters_ = 0;
+  have_weights_ = false;
+  alloc_store(n_cells);
+  const int kg = T_.k_gram;
+  // corners: bring to the device (host path) or use in place (device path); H from cell 0
+  const double *dc = corners;
+  const long long *dids = (const long long *)cell_ids;
+  double c0[24];
+  if (!device_ptrs) {
+    CUDA_OK(cudaMemcpyAsync(d_corners_, corners, (size_t)n_cells * 24 * sizeof(double), cudaMemcpyHostToDevice, stream_));
+    dc = d_corners_;
+    if (cell_ids) {
+      CUDA_OK(cudaMemcpyAsync(d_ids_, cell_ids, (size_t)n_cells * sizeof(long long), cudaMemcpyHostToDevice, stream_));
+      dids = d_ids_;
+    }
+    std::memcpy(c0, corners, sizeof(c0));
+  } else {
+    CUDA_OK(cudaMemcpy(c0, corners, sizeof(c0), cudaMemcpyDeviceToHost));
+  }
+  const double H = c0[21] - c0[0];   // vertex 7 - vertex 0, x
+  if (!(H > 0)) throw std::invalid_argument("coarse cell 0 has non-positive edge length");
+  const double h = H / T_.n;
+  const double kscale = std::pow(h, T_.k_h_exponent), f1scale = std::pow(H, T_.f1_H_exponent);
+  const int cpb = spec_.p.cells_per_batch > 0 ? spec_.p.cells_per_batch : 4096;
+  const int batch_cells = std::min(n_cells, (cpb + kLanes - 1) / kLanes * kLanes);
+  alloc_batch((batch_cells + kLanes - 1) / kLanes);
+  CUDA_OK(cudaMemsetAsync(d_flag_, 0, 2 * sizeof(int), stream_));
+  float ms_asm = 0, ms_lift = 0, ms_solve = 0, ms_gram = 0;
+  double ms_spmm = 0;
+  long total_it = 0;
+  CUDA_OK(cudaEventRecord(ev_[6], stream_));
+  for (int cell0 = 0; cell0 < n_cells; cell0 += batch_cells) {
+    const int nb = std::min(batch_cells, n_cells - cell0);
+    const int groups = (nb + kLanes - 1) / kLanes;
+    last_batch_cell0_ = cell0; last_batch_n_ = nb;
+    CUDA_OK(cudaEventRecord(ev_[0], stream_));
+    k_prepare_cells<<<(groups * kLanes + 127) / 128, 128, 0, stream_>>>(dc, dids, cell0, nb, n_cells, H, d_x0_, d_gid_, d_flag_ + 1);
+    k_sample_coefficients<<<dim3(T_.nC, groups), dim3(kLanes, 8), 0, stream_>>>(spec_.coef, d_prog_, d_x0_, d_gid_, h, d_coef_, d_fr_);
+    k_assemble_slots<<<dim3((T_.asm00.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
+        asm00_.dev, T_.nC, d_coef_, std::pow(h, T_.asm00.h_exponent) / 8.0, d_vals_, n_slots_, 0);
+    launches_ += 3;
+    if (T_.asm11.n_slots) {
+      k_assemble_slots<<<dim3((T_.asm11.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
+          asm11_.dev, T_.nC, d_coef_, std::pow(h, T_.asm11.h_exponent) / 8.0, d_vals_, n_slots_, T_.n_slots0);
+      ++launches_;
+    }
+    k_assemble_slots<<<dim3((T_.asm_rhs.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
+        asmrhs_.dev, T_.nC, d_fr_, std::pow(h, T_.asm_rhs.h_exponent) / 8.0, d_grhs_, T_.asm_rhs.n_slots, 0);
+    k_build_precond<<<dim3((T_.NI + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
+        T_.blk[0].n_int, T_.NI, n_slots_, d_diag0_, d_diag1_, kint_.dev, kscale, d_vals_, d_minv_);
+    CUDA_OK(cudaEventRecord(ev_[1], stream_));
+    k_lift_rhs<<<dim3((T_.NI + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(
+        lift_.dev, T_.NI, T_.NB, T_.k_solve, n_slots_, kscale, f1scale, d_vals_, d_G_, d_F1_, d_vec_[2]);
+    launches_ += 3;
+    CUDA_OK(cudaEventRecord(ev_[2], stream_));
+    { const int itb = solve_batch(groups, nb, kscale, st, ms_spmm); total_it += itb; cell_iters_ += (double)itb * nb; }
+    CUDA_OK(cudaEventRecord(ev_[3], stream_));
+    const int gz0 = cell0 / kLanes;
+    BasisDims D{T_.blk[0].n_int, T_.two_blocks ? T_.blk[1].n_int : 0, T_.blk[0].n_total,
+                T_.two_blocks ? T_.blk[1].n_total : 0, T_.blk[0].n_total - T_.blk[0].n_int, T_.NI, T_.NB, T_.NF,
+                T_.k_solve, kg, T_.k0, T_.pairing == MSFEC_RT_DQ ? 1 : 0};
+    k_finalize_basis<<<dim3((T_.NF + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(D, d_vec_[7], d_G_, d_Z_, gz0);
+    k_apply_full<<<dim3((T_.NF + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(full_.dev, T_.NF, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
+    const int rhs_off = T_.rhs_block ? T_.blk[0].n_total : 0;
+    k_gram<<<dim3(kg, groups), dim3(kLanes, kg), 0, stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
+                                                            cell0, n_cells, d_M_, d_r_);
+    launches_ += 3;
+    CUDA_OK(cudaEventRecord(ev_[4], stream_));
+    CUDA_OK(cudaStreamSynchronize(stream_));
+    float ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev_[0], ev_[1])); ms_asm += ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev_[1], ev_[2])); ms_lift += ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev_[2], ev_[3])); ms_solve += ms;
+    CUDA_OK(cudaEventElapsedTime(&ms, ev_[3], ev_[4])); ms_gram += ms;
+  }
+  if (device_ptrs) {
+    CUDA_OK(cudaMemcpyAsync(elem_matrix, d_M_, (size_t)n_cells * kg * kg * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+    CUDA_OK(cudaMemcpyAsync(elem_rhs, d_r_, (size_t)n_cells * kg * sizeof(double), cudaMemcpyDeviceToDevice, stream_));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(elem_matrix, d_M_, (size_t)n_cells * kg * kg * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+    CUDA_OK(cudaMemcpyAsync(elem_rhs, d_r_, (size_t)n_cells * kg * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  }
+  CUDA_OK(cudaMemcpyAsync(h_flag_, d_flag_, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaEventRecord(ev_[7], stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  CUDA_OK(cudaGetLastError());
+  if (h_flag_[1]) throw std::invalid_argument("coarse cell " + std::to_string(h_flag_[1] - 1) +
+                                              " is not an axis-aligned cube of the common edge length");
+  float ms_total;
+  CUDA_OK(cudaEventElapsedTime(&ms_total, ev_[6], ev_[7]));
+  st.iterations_mean /= std::max<double>(1.0, (double)n_cells * T_.k_solve);
+  st.kernel_launches = (int)launches_;
+  st.ms_assemble = ms_asm; st.ms_lift = ms_lift; st.ms_solve = ms_solve; st.ms_gram = ms_gram; st.ms_total = ms_total;
+  // algorithmic bytes of the Krylov kernel ("compulsory" figure): each per-cell matrix
+  // value of the interior system read once per executed iteration + rhs read once + solution written once.
+  st.krylov_matrix_bytes = 8.0 * (double)T_.sys.cref.size() * cell_iters_ + 2.0 * 8.0 * T_.k_solve * (double)T_.NI * n_cells;
+  st.krylov_spmm_launches = total_it;
+  st.krylov_ms_spmm = spmm_samples_ ? ms_spmm / spmm_samples_ : 0.0;   // mean duration of one SpMM launch
+  if (stats) *stats = st;
+  return st.not_converged ? MSFEC_ENOTCONVERGED : MSFEC_OK;
+}
+
+void Engine::set_weights(int n_cells, const double *weights) {
+  CUDA_OK(cudaSetDevice(device_));
+  if (!d_Z_ || n_cells != store_cells_) throw std::logic_error("set_weights: no matching basis build");
+  const size_t L = kLanes * sizeof(double);
+  if (!d_U_) CUDA_OK(cudaMalloc(&d_U_, (size_t)store_groups_ * T_.NF * L));
+  if (!d_w_) CUDA_OK(cudaMalloc(&d_w_, (size_t)store_cells_ * T_.k_gram * sizeof(double)));
+  CUDA_OK(cudaMemcpyAsync(d_w_, weights, (size_t)n_cells * T_.k_gram * sizeof(double), cudaMemcpyHostToDevice, stream_));
+  k_combine<<<dim3((T_.NF + 7) / 8, store_groups_), dim3(kLanes, 8), 0, stream_>>>(T_.NF, T_.k_gram, n_cells, d_Z_, d_w_, d_U_);
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  CUDA_OK(cudaGetLastError());
+  have_weights_ = true;
+}
+
+static void fetch_strided(const double *dsrc, size_t first, size_t stride_elems, int count, double *hdst) {
+  if (!hdst || count <= 0) return;
+  CUDA_OK(cudaMemcpy2D(hdst, sizeof(double), dsrc + first, stride_elems * sizeof(double), sizeof(double), count,
+                       cudaMemcpyDeviceToHost));
+}
+
+void Engine::get_fine_solution(int cell, double *b0, double *b1) {
+  CUDA_OK(cudaSetDevice(device_));
+  if (!have_weights_) throw std::logic_error("get_fine_solution: set_weights has not been called");
+  if (cell < 0 || cell >= store_cells_) throw std::invalid_argument("cell out of range");
+  const size_t g = cell / kLanes, lane = cell % kLanes;
+  fetch_strided(d_U_, (g * T_.NF) * kLanes + lane, kLanes, T_.blk[0].n_total, b0);
+  if (T_.two_blocks) fetch_strided(d_U_, (g * T_.NF + T_.blk[0].n_total) * kLanes + lane, kLanes, T_.blk[1].n_total, b1);
+}
+
+void Engine::get_basis(int cell, int basis, double *b0, double *b1) {
+  CUDA_OK(cudaSetDevice(device_));
+  if (!d_Z_ || cell < 0 || cell >= store_cells_) throw std::invalid_argument("cell out of range / no build");
+  if (basis < 0 || basis >= T_.k_gram) throw std::invalid_argument("basis index out of range");
+  const size_t g = cell / kLanes, lane = cell % kLanes, kg = T_.k_gram;
+  fetch_strided(d_Z_, ((g * T_.NF) * kg + basis) * kLanes + lane, kg * kLanes, T_.blk[0].n_total, b0);
+  if (T_.two_blocks)
+    fetch_strided(d_Z_, ((g * T_.NF + T_.blk[0].n_total) * kg + basis) * kLanes + lane, kg * kLanes, T_.blk[1].n_total, b1);
+}
+
+void Engine::cell_values(int cell, double *values, size_t *count) {
+  CUDA_OK(cudaSetDevice(device_));
+  const size_t total = (size_t)n_slots_ + T_.asm_rhs.n_slots;
+  if (!values) { *count = total; return; }
+  if (cell < last_batch_cell0_ || cell >= last_batch_cell0_ + last_batch_n_)
+    throw std::invalid_argument("cell is not part of the last resident batch");
+  const size_t c = cell - last_batch_cell0_, g = c / kLanes, lane = c % kLanes;
+  fetch_strided(d_vals_, (g * n_slots_) * kLanes + lane, kLanes, n_slots_, values);
+  fetch_strided(d_grhs_, (g * T_.asm_rhs.n_slots) * kLanes + lane, kLanes, T_.asm_rhs.n_slots, values + n_slots_);
+  *count = total;
+}
+
+// ------------------------------------------------------------------------------------
+Engine *engine_create(int device, const ProblemSpec &spec, const Topology &topo) { return new Engine(device, spec, topo); }
+void engine_destroy(Engine *e) { delete e; }
+
+#define GUARD(body)                                                                \
+  try { body; }                                                                    \
+  catch (const std::invalid_argument &ex) { err = ex.what(); return MSFEC_EINVAL; } \
+  catch (const std::logic_error &ex) { err = ex.what(); return MSFEC_ESTATE; }      \
+  catch (const std::bad_alloc &) { err = "out of host memory"; return MSFEC_ENOMEM; } \
+  catch (const std::exception &ex) { err = ex.what(); return MSFEC_ECUDA; }
+
+int engine_build(Engine *e, int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix,
+                 double *elem_rhs, bool device_ptrs, msfec_stats *stats, std::string &err) {
+  GUARD({
+    const int rc = e->build(n_cells, corners, cell_ids, elem_matrix, elem_rhs, device_ptrs, stats);
+    if (rc == MSFEC_ENOTCONVERGED) err = "Krylov solve hit the iteration cap for some right-hand sides";
+    return rc;
+  })
+}
+int engine_set_weights(Engine *e, int n_cells, const double *weights, std::string &err) {
+  GUARD({ e->set_weights(n_cells, weights); return MSFEC_OK; })
+}
+int engine_get_fine_solution(Engine *e, int cell, double *b0, double *b1, std::string &err) {
+  GUARD({ e->get_fine_solution(cell, b0, b1); return MSFEC_OK; })
+}
+int engine_get_basis(Engine *e, int cell, int basis, double *b0, double *b1, std::string &err) {
+  GUARD({ e->get_basis(cell, basis, b0, b1); return MSFEC_OK; })
+}
+int engine_cell_values(Engine *e, int cell, double *values, size_t *count, std::string &err) {
+  GUARD({ e->cell_values(cell, values, count); return MSFEC_OK; })
+}
+
+}  // namespace msfec

@@ -1,0 +1,83 @@
+// Shared fine-grid topology, sparsity patterns and assembly tables.
+//
+// Every coarse cell of the reference is refined identically
+// (GridGenerator::general_cell + refine_global, reference
+// source/Ned_RT/ned_rt_basis.cc:167-179) and gets the same FESystem, DoF enumeration,
+// sparsity pattern and boundary-constraint structure (:181-359).  The reference redoes
+// that setup for every cell; here it is done ONCE per (pairing, n) on the host and all
+// coarse cells share it.  Only matrix *values* (the "slots") differ between cells.
+//
+// Numbering: each block (sigma-type = block 0, u-type = block 1) numbers its interior
+// DoFs first, then its boundary (essential-BC) DoFs.  Fine DoF numbering never leaves
+// the reference's basis object, so this choice is free.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace msfec {
+
+enum EntityKind { ENT_V = 0, ENT_E = 1, ENT_F = 2, ENT_C = 3 };
+
+struct BlockTopo {
+  int kind = 0;
+  int ldofs = 0;                 // local DoFs per fine cell: 8 / 12 / 6 / 1
+  int n_total = 0, n_int = 0;
+  std::vector<int32_t> cell_dofs;   // [nC][ldofs] -> index in interior-first numbering
+  std::vector<double> pos;          // [n_total][3], units of h (edge midpoints, face centres)
+  std::vector<int32_t> axis;        // [n_total] direction of edge / face normal, -1 otherwise
+  std::vector<uint8_t> bnd;         // [n_total]
+};
+
+// value = scale * sum_{contrib of slot} sum_{e in pair list} w_e * coef[fine cell][idx_e]
+struct AsmTable {
+  int n_slots = 0;
+  int coef_stride = 0;                  // coefficient channels per fine cell (8*7 or 8*ncomp)
+  std::vector<int32_t> contrib_ptr;     // [n_slots+1]
+  std::vector<int32_t> contrib_cell;    // fine cell
+  std::vector<int32_t> contrib_pair;    // index into pair_ptr
+  std::vector<int32_t> pair_ptr;        // [n_pairs+1]
+  std::vector<int32_t> pair_idx;        // coefficient channel (q*ncomp + comp)
+  std::vector<double> pair_w;
+  int h_exponent = 0;                   // scale = h^h_exponent / 8
+};
+
+// CSR operator whose entries reference per-cell slots (cell part) or cell-independent
+// values (shared part, to be multiplied by kscale = h^k_h_exponent).
+struct RefOperator {
+  int n_rows = 0, n_cols = 0;
+  std::vector<int32_t> cptr, ccol, cref;   // cref = (slot << 1) | negate
+  std::vector<int32_t> sptr, scol;
+  std::vector<double> sval;
+};
+
+struct Topology {
+  int pairing = 0, n = 0, nC = 0;
+  int k_solve = 0, k_gram = 0, k0 = 0;     // k0 = number of sigma-type coarse functions
+  bool two_blocks = false;
+  BlockTopo blk[2];
+  int NI = 0, NB = 0, NF = 0;              // interior / boundary / full sizes over both blocks
+  int n_slots0 = 0, n_slots1 = 0;          // A00 slots, A11 slots (slot space = [A00 | A11])
+  AsmTable asm00, asm11, asm_rhs;          // asm_rhs: one "slot" per u-type DoF (all DoFs for Q)
+  int coef_tensor_is_inverse = 0;          // tensor channel holds A^{-1} (else A)
+  int coef_scalar_is_inverse = 0;          // scalar channel holds 1/B (else B)
+  int rhs_ncomp = 1;
+  int k_h_exponent = 0;                    // K ~ h^p
+  int f1_H_exponent = 0;                   // F1 (unit-H table) scales with H^p
+  RefOperator sys;                         // interior saddle system, symmetric form [A00 -K^T; -K -A11]
+  RefOperator lift;                        // rows = interior, cols = boundary DoFs [B0 | B1]
+  RefOperator full;                        // rows/cols = all DoFs [all0 | all1], form [A00 -K^T; K A11]
+  RefOperator kint;                        // K restricted to interior rows (blk1) x interior cols (blk0)
+  std::vector<int32_t> diag_slot0, diag_slot1;   // slot of (r,r) for interior rows of each block (-1: none)
+  std::vector<double> G;                   // [k_solve][NB] essential boundary data (H-independent)
+  std::vector<double> F1;                  // [k_solve][NI] volume rhs of the symmetric-form system, unit H
+  int rhs_block = 0;                       // block the global rhs lives on
+};
+
+// Builds everything above.  pairing: enum msfec_pairing; n = 2^L.
+Topology build_topology(int pairing, int n);
+
+// Quadrature abscissae of QGauss<3>(2) on the unit cube, x fastest.
+void gauss_points(double qp[8][3]);
+
+}  // namespace msfec

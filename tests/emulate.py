@@ -1,0 +1,104 @@
+"""numpy emulation of the device pipeline driven by the HOST-BUILT tables of
+libmsfec_b200.so (msfec_debug_table).  Test infrastructure: lets the CPU-only test
+suite check the topology / assembly / operator tables (what the CUDA kernels consume)
+against the oracle without a GPU.  The arithmetic mirrors csrc/engine.cu kernel by
+kernel; the Krylov solve is replaced by a sparse direct solve."""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from oracle import msfec_oracle as mo
+
+
+def dims_of(bb):
+    import importlib
+    d = bb.table("dims")
+    from conftest import msfec_mod
+    return dict(zip(msfec_mod().DIMS, d.tolist()))
+
+
+def coef_channels(prob: "mo.Problem", corners, cell_gid, D):
+    x0 = np.asarray(corners)[0]
+    H = corners[7][0] - x0[0]
+    A, Ainv, B, pts = mo.coefficient_fields(prob, x0, H, cell_gid)
+    Tn = Ainv if D["tensor_inverse"] else A
+    s = 1.0 / B if D["scalar_inverse"] else B
+    nC = Tn.shape[0]
+    coef = np.zeros((nC, 8, 7))
+    c = 0
+    for a in range(3):
+        for b in range(a, 3):
+            coef[:, :, c] = Tn[:, :, a, b]; c += 1
+    coef[:, :, 6] = s
+    exprs = [mo.Expr(e, prob.rhs_constants) for e in prob.rhs_expr.split(";")]
+    fr = np.stack([e(pts) for e in exprs], -1)          # [nC, 8, ncomp]
+    return coef.reshape(nC, 56), fr.reshape(nC, -1), H
+
+
+def assemble_slots(bb, prefix, coef, scale):
+    cp = bb.table(prefix + ".contrib_ptr"); cc = bb.table(prefix + ".contrib_cell"); cpair = bb.table(prefix + ".contrib_pair")
+    pp = bb.table(prefix + ".pair_ptr"); pi = bb.table(prefix + ".pair_idx"); pw = bb.table(prefix + ".pair_w")
+    n_slots = len(cp) - 1
+    out = np.zeros(n_slots)
+    # per-contribution value
+    npairs = len(pp) - 1
+    # value of pair p on every fine cell: sum_e w_e coef[T, idx_e]
+    pv = np.zeros((coef.shape[0], npairs))
+    for p in range(npairs):
+        sl = slice(pp[p], pp[p + 1])
+        if pp[p + 1] > pp[p]:
+            pv[:, p] = coef[:, pi[sl]] @ pw[sl]
+    vals = pv[cc, cpair]
+    slot_of = np.repeat(np.arange(n_slots), np.diff(cp))
+    np.add.at(out, slot_of, vals)
+    return out * scale
+
+
+def ref_operator(bb, name, vals, kscale, shape):
+    cptr = bb.table(name + ".cptr"); ccol = bb.table(name + ".ccol"); cref = bb.table(name + ".cref")
+    sptr = bb.table(name + ".sptr"); scol = bb.table(name + ".scol"); sval = bb.table(name + ".sval")
+    n_rows = len(cptr) - 1
+    rows_c = np.repeat(np.arange(n_rows), np.diff(cptr))
+    v_c = np.where(cref & 1, -1.0, 1.0) * vals[cref >> 1] if len(cref) else np.zeros(0)
+    rows_s = np.repeat(np.arange(n_rows), np.diff(sptr))
+    A = sp.coo_matrix((np.concatenate([v_c, sval * kscale]),
+                       (np.concatenate([rows_c, rows_s]), np.concatenate([ccol, scol]))), shape=shape)
+    return A.tocsr()
+
+
+def emulate_cell(bb, prob, corners, cell_gid=0):
+    """Returns M, r, Z (full basis store [NF, kg]) computed from the library's tables."""
+    D = dims_of(bb)
+    coef, fr, H = coef_channels(prob, corners, cell_gid, D)
+    h = H / D["n"]
+    v00 = assemble_slots(bb, "asm00", coef, h ** D["asm00_h_exponent"] / 8.0)
+    v11 = assemble_slots(bb, "asm11", coef, h ** D["asm11_h_exponent"] / 8.0) if D["n_slots1"] else np.zeros(0)
+    vals = np.concatenate([v00, v11])
+    grhs = assemble_slots(bb, "asm_rhs", fr, h ** D["asm_rhs_h_exponent"] / 8.0)
+    kscale = h ** D["k_h_exponent"]; f1scale = H ** D["f1_H_exponent"]
+    NI, NB, NF, k, kg, k0 = D["NI"], D["NB"], D["NF"], D["k_solve"], D["k_gram"], D["k0"]
+    Sys = ref_operator(bb, "sys", vals, kscale, (NI, NI))
+    Lift = ref_operator(bb, "lift", vals, kscale, (NI, NB))
+    Full = ref_operator(bb, "full", vals, kscale, (NF, NF))
+    G = bb.table("G").reshape(k, NB); F1 = bb.table("F1").reshape(k, NI)
+    b = F1.T * f1scale + Lift @ G.T
+    if D["pairing"] == 3:   # RT_DQ: singular (constant u); pin last unknown for the direct emulation
+        keep = np.arange(NI - 1)
+        x = np.zeros((NI, k))
+        x[keep] = spla.splu(Sys[keep][:, keep].tocsc()).solve(b[keep])
+    else:
+        x = spla.splu(Sys.tocsc()).solve(b)
+    NI0, N0, NI1, N1 = D["NI0"], D["N0"], D["NI1"], D["N1"]
+    NB0 = N0 - NI0
+    Z = np.zeros((NF, kg))
+    for j in range(kg):
+        if j < k0:
+            Z[:NI0, j] = x[:NI0, j]; Z[NI0:N0, j] = G[j, :NB0]
+        elif D["pairing"] == 3:
+            Z[N0:, j] = 1.0
+        else:
+            Z[N0:N0 + NI1, j] = x[NI0:, j]; Z[N0 + NI1:, j] = G[j, NB0:]
+    M = Z.T @ (Full @ Z)
+    off = N0 if D["rhs_block"] else 0
+    r = Z[off:off + len(grhs)].T @ grhs
+    return M, r, Z, dict(vals=vals, grhs=grhs, Sys=Sys, b=b, x=x)

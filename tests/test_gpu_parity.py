@@ -1,0 +1,141 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the same inputs.
+Tolerance (north star): coarse element matrices to relative 1e-9 (max-norm scaled by max |M|).
+Run with:  gpurun -- python -m pytest tests -m gpu -x -q"""
+import os
+
+import numpy as np
+import pytest
+
+from common import ROOT, lib_problem, oracle_problem, rel_err
+from oracle import msfec_oracle as mo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _check_cells(bb, prob, cells, ids, which):
+    M = bb.get_global_element_matrix(); r = bb.get_global_element_rhs()
+    worst = 0.0
+    for c in which:
+        Mo, ro, *_ = mo.build_basis(prob, cells[c], int(ids[c]))
+        worst = max(worst, rel_err(M[c], Mo), float(np.abs(r[c] - ro).max() / max(np.abs(ro).max(), 1e-300)))
+    return worst
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+@pytest.mark.parametrize("L", [2, 3])
+def test_prm_coefficients_match_oracle(msfec, pairing, L):
+    """configs[0..3] coefficients (examples/prm == reference test-01 files) on the 64-cell coarse mesh."""
+    cells = mo.morton_cells(2)
+    ids = np.arange(64)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L), device=0).run(cells, ids)
+    worst = _check_cells(bb, oracle_problem(pairing, L), cells, ids, (0, 21, 37, 63))
+    print(pairing, L, "worst", worst, bb.stats)
+    assert worst < TOL
+    assert bb.stats["not_converged"] == 0 and bb.stats["kernel_launches"] > 0
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_golden_fixtures(msfec, pairing):
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "oracle_elem_matrices.npz"))
+    cells = mo.morton_cells(2)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, 2), device=0).run(cells)
+    for c in (5, 37):
+        assert rel_err(bb.get_global_element_matrix()[c], gold[f"{pairing}_M_{c}"]) < TOL
+        ro = gold[f"{pairing}_r_{c}"]
+        assert np.abs(bb.get_global_element_rhs()[c] - ro).max() <= TOL * max(np.abs(ro).max(), 1e-300)
+
+
+def test_random_field_ragged_batches(msfec):
+    """C5-style rough field; 70 cells = 2 full lane groups + a ragged one, split over 2 batches."""
+    cells = mo.morton_cells(3)[100:170]
+    ids = np.arange(100, 170)
+    p = lib_problem(msfec, "NED_RT", 2, random_seed=20261017, cells_per_batch=64)
+    bb = msfec.BasisBuilder(p, device=0).run(cells, ids)
+    worst = _check_cells(bb, oracle_problem("NED_RT", 2, random_seed=20261017), cells, ids, (0, 31, 32, 63, 64, 69))
+    assert worst < TOL
+
+
+def test_single_cell_and_basis_vectors(msfec):
+    """n_cells = 1 (31 padded lanes) and the fine-scale basis functions themselves."""
+    cells = mo.morton_cells(2)[37:38]
+    bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 2), device=0).run(cells, np.array([37]))
+    prob = oracle_problem("NED_RT", 2)
+    Mo, ro, X0, X1, cs = mo.build_basis(prob, cells[0], 37)
+    assert rel_err(bb.get_global_element_matrix()[0], Mo) < TOL
+    # map library numbering -> oracle numbering through entity positions
+    g = mo.fine_grid(prob.n)
+    for blk, (opos, Xo) in enumerate(((g.e_pos, X0), (g.f_pos, X1))):
+        pos, axis, bnd = bb.layout(blk)
+        key = {tuple(np.round(p_ * 2).astype(int)): i for i, p_ in enumerate(opos)}
+        perm = np.array([key[tuple(np.round(p_ * 2).astype(int))] for p_ in pos])
+        for j in ((0, 5, 11) if blk == 0 else (12, 17)):
+            b0, b1 = bb.get_basis(0, j)
+            mine = b0 if blk == 0 else b1
+            assert rel_err(mine, Xo[j][perm]) < 1e-8
+    # set_global_weights: u_fine = sum_i w_i b_i
+    w = np.random.default_rng(1).standard_normal((1, 18))
+    bb.set_global_weights(w)
+    u0, u1 = bb.get_fine_solution(0)
+    ref0 = sum(w[0, j] * bb.get_basis(0, j)[0] for j in range(18))
+    ref1 = sum(w[0, j] * bb.get_basis(0, j)[1] for j in range(18))
+    assert rel_err(u0, ref0) < 1e-13 and rel_err(u1, ref1) < 1e-13
+
+
+def test_constant_coefficient_reproduction_on_gpu(msfec):
+    """Invariant 3 through the CUDA path: constant diagonal A -> M equals the L=0 analytic matrix."""
+    cells = mo.morton_cells(1)
+    for pairing in mo.PAIRINGS:
+        rhs = b"1;2;3" if pairing in ("Q_NED", "NED_RT") else b"1"
+        p = msfec.make_problem(pairing, n_refine_local=3, a_rotate=0, a_scale=(2.0, 3.0, 0.5), a_freq=(0, 0, 0),
+                               b_expression=b"1.7", rhs_expression=rhs)
+        bb = msfec.BasisBuilder(p, device=0).run(cells)
+        prob0 = mo.Problem(pairing=pairing, n_refine_local=0, a_freq=(0, 0, 0), a_scale=(2.0, 3.0, 0.5),
+                           a_rotate=False, b_expr="1.7", rhs_expr=rhs.decode())
+        for c in (0, 7):
+            M0, r0, *_ = mo.build_basis(prob0, cells[c], c)
+            assert rel_err(bb.get_global_element_matrix()[c], M0) < TOL
+
+
+def test_structure_properties_at_scale(msfec):
+    """Size-independent properties on 1024 random-field cells (no oracle solve needed)."""
+    cells = mo.morton_cells(4)[:1024]
+    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017)
+    bb = msfec.BasisBuilder(p, device=0).run(cells)
+    M = bb.get_global_element_matrix()
+    s = np.abs(M).max(axis=(1, 2))
+    assert np.isfinite(M).all()
+    assert (np.abs(M[:, :12, :12] - M[:, :12, :12].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    assert (np.abs(M[:, 12:, 12:] - M[:, 12:, 12:].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    assert (np.abs(M[:, :12, 12:] + M[:, 12:, :12].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    # a few cells against the oracle
+    prob = oracle_problem("NED_RT", 3, random_seed=20261017)
+    worst = _check_cells(bb, prob, cells, np.arange(1024), (0, 517, 1023))
+    print("C5-style worst", worst, bb.stats)
+    assert worst < TOL
+
+
+def test_error_paths(msfec):
+    p = lib_problem(msfec, "Q", 2)
+    bb = msfec.BasisBuilder(p, device=0)
+    cells = mo.morton_cells(1).copy()
+    cells[3, 5, 1] += 0.01          # not a cube any more
+    with pytest.raises(msfec.MsfecError) as e:
+        bb.run(cells)
+    assert e.value.code == 1
+    with pytest.raises(msfec.MsfecError):
+        bb.set_global_weights(np.zeros((3, 8)))      # wrong cell count
+
+
+def test_device_pointer_entry(msfec):
+    import torch
+    cells = mo.morton_cells(2)
+    p = lib_problem(msfec, "Q", 3)
+    bb = msfec.BasisBuilder(p, device=0)
+    dc = torch.tensor(cells, dtype=torch.float64, device="cuda:0").contiguous()
+    dM = torch.empty((64, 8, 8), dtype=torch.float64, device="cuda:0")
+    dr = torch.empty((64, 8), dtype=torch.float64, device="cuda:0")
+    bb.run_device(64, dc.data_ptr(), 0, dM.data_ptr(), dr.data_ptr())
+    torch.cuda.synchronize()
+    host = msfec.BasisBuilder(p, device=0).run(cells)
+    assert rel_err(dM.cpu().numpy(), host.get_global_element_matrix()) < 1e-12

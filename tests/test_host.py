@@ -1,0 +1,126 @@
+"""CPU tests of the host side of libmsfec_b200.so: ABI surface, .prm reader, shared topology and
+assembly/operator tables (validated by a numpy emulation of the device pipeline against the oracle).
+No compute entry point is exercised here; those need a GPU (tests/test_gpu_parity.py)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import emulate
+from common import ROOT, lib_problem, oracle_problem, prm_path, rel_err
+from oracle import msfec_oracle as mo
+
+
+def test_library_exports_every_declared_symbol(msfec):
+    hdr = open(os.path.join(ROOT, "include", "msfec.h")).read()
+    declared = set(re.findall(r"\b(msfec_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"msfec_ctx"}
+    assert declared, "no declarations parsed"
+    lib = msfec.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/msfec.h but not exported"
+    assert set(msfec.EXPORTS) == declared
+    assert lib.msfec_abi_version() == 1
+
+
+def test_struct_layout_matches_header(msfec):
+    # sizeof checks guard the ctypes mirror against drift
+    assert C.sizeof(msfec.Problem) == 4 * 6 + 4 * 3 + 4 + 8 * 3 * 2 + 8 * 2 + 8 * 3 + 8 + 8 + 8 + 4 + 4
+    assert C.sizeof(msfec.Stats) == 4 * 8 + 8 * 9 + 8
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_prm_reader_matches_oracle_reader(msfec, pairing):
+    p = msfec.problem_from_prm(prm_path(pairing), pairing)
+    o = mo.Problem.from_prm(prm_path(pairing), pairing)
+    assert p.n_refine_local == o.n_refine_local == 4 and p.n_refine_global == 2
+    assert tuple(p.a_freq) == o.a_freq and tuple(p.a_alpha) == o.a_alpha and bool(p.a_rotate) == o.a_rotate
+    assert p.rhs_expression.decode() == o.rhs_expr
+    if pairing in ("Q_NED", "NED_RT"):
+        assert p.b_expression.decode() == o.b_expr and p.b_freq == 14
+
+
+def test_prm_errors(msfec, tmp_path):
+    bad = tmp_path / "bad.prm"
+    bad.write_text("subsection A\n set x = 1\n")
+    with pytest.raises(msfec.MsfecError) as e:
+        msfec.problem_from_prm(str(bad), "Q")
+    assert e.value.code == 7
+    with pytest.raises(msfec.MsfecError):
+        msfec.problem_from_prm(str(tmp_path / "missing.prm"), "Q")
+
+
+def test_shape_queries(msfec):
+    lib = msfec.lib()
+    assert [lib.msfec_k(i) for i in range(4)] == [8, 20, 18, 7]
+    n0, n1 = C.c_int(), C.c_int()
+    assert lib.msfec_n_fine_dofs(2, 3, C.byref(n0), C.byref(n1)) == 3672 and (n0.value, n1.value) == (1944, 1728)
+    assert lib.msfec_n_fine_dofs(2, 4, C.byref(n0), C.byref(n1)) == 26928
+
+
+def test_entity_counts_match_survey(msfec):
+    """n=8: boundary E 768, F 384; nnz EE 53 400, FF 17 088, EF 31 488."""
+    bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 3), device=-1)
+    D = emulate.dims_of(bb)
+    assert (D["N0"], D["N1"], D["N0"] - D["NI0"], D["N1"] - D["NI1"]) == (1944, 1728, 768, 384)
+    assert 2 * D["n_slots0"] - D["N0"] == 53400 and 2 * D["n_slots1"] - D["N1"] == 17088
+    # the coupling block keeps only numerically non-zero entries (structural count is 31 488)
+    full_shared = len(bb.table("full.scol"))
+    assert full_shared == 2 * 19200 and full_shared <= 2 * 31488
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+@pytest.mark.parametrize("L", [1, 2])
+def test_tables_reproduce_oracle(msfec, pairing, L):
+    """Slots, operators, boundary data and volume rhs built by csrc/topology.cpp give the oracle's
+    coarse matrices when driven through the same arithmetic as the kernels."""
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L), device=-1)
+    cells = mo.morton_cells(2)
+    prob = oracle_problem(pairing, L)
+    M, r, Z, _ = emulate.emulate_cell(bb, prob, cells[37], 37)
+    Mo, ro, X0, X1, cs = mo.build_basis(prob, cells[37], 37)
+    assert rel_err(M, Mo) < 1e-11
+    assert np.abs(r - ro).max() <= 1e-12 * max(1.0, np.abs(ro).max())
+
+
+def test_tables_random_field(msfec):
+    bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 2, random_seed=20261017), device=-1)
+    cells = mo.morton_cells(3)
+    prob = oracle_problem("NED_RT", 2, random_seed=20261017)
+    M, r, *_ = emulate.emulate_cell(bb, prob, cells[100], 100)
+    Mo, ro, *_ = mo.build_basis(prob, cells[100], 100)
+    assert rel_err(M, Mo) < 1e-11
+
+
+def test_no_cpu_fallback(msfec):
+    """Compute entry points must fail loudly without a device."""
+    bb = msfec.BasisBuilder(lib_problem(msfec, "Q", 1), device=-1)
+    with pytest.raises(msfec.MsfecError) as e:
+        bb.run(mo.morton_cells(1))
+    assert e.value.code == 2
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if not has_gpu:
+        with pytest.raises(msfec.MsfecError) as e2:
+            msfec.BasisBuilder(lib_problem(msfec, "Q", 1), device=0)
+        assert e2.value.code == 2
+
+
+def test_invalid_arguments(msfec):
+    p = lib_problem(msfec, "Q", 1)
+    p.n_refine_local = 0
+    with pytest.raises(msfec.MsfecError) as e:
+        msfec.BasisBuilder(p, device=-1)
+    assert e.value.code == 1
+    p = lib_problem(msfec, "NED_RT", 1, rhs_expression=b"1")      # needs 3 components
+    with pytest.raises(msfec.MsfecError):
+        msfec.BasisBuilder(p, device=-1)
+    p = lib_problem(msfec, "Q", 1, rhs_expression=b"foo(x)")
+    with pytest.raises(msfec.MsfecError) as e:
+        msfec.BasisBuilder(p, device=-1)
+    assert e.value.code == 7
