@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""Basis-build benchmark (BASELINE.json metric: coarse cells/s and fine DoF-solves/s).
+
+Workload (config 5 of BASELINE.json): synthetic 3D Ned_RT, rough random-field coefficient,
+32^3 coarse cells x 3 local refinements.  The 32 768 coarse cells are enumerated in p4est Morton
+order and split into contiguous chunks, one per rank/GPU (the reference's is_locally_owned
+partition); the basis build needs no inter-GPU traffic, so there is no data-path collective --
+torch.distributed (NCCL) is used for the barriers and the max-over-ranks reduction only.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells C]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one full pass of the hot path (assemble -> lift -> Krylov solve of all k rhs -> Gram)
+over this rank's cells.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20261017
+RHS = "scale*(2*x-1)*(y^2-y)*(z^2-z); scale*(2*y-1)*(x^2-x)*(z^2-z); scale*(2*z-1)*(x^2-x)*(y^2-y)"
+
+
+def load_binding():
+    spec = importlib.util.spec_from_file_location("msfec_b200", os.path.join(ROOT, "mpi-msfec_b200", "msfec_b200.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["msfec_b200"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def morton_cells(g_ref, lo, hi):
+    """corners[hi-lo, 8, 3] of coarse cells lo..hi-1 in p4est z-order (host logic, no oracle import)."""
+    idx = np.arange(lo, hi, dtype=np.int64)
+    ijk = np.zeros((idx.size, 3), dtype=np.int64)
+    for b in range(g_ref):
+        for d in range(3):
+            ijk[:, d] |= ((idx >> (3 * b + d)) & 1) << b
+    H = 1.0 / (1 << g_ref)
+    off = np.array([[v & 1, (v >> 1) & 1, v >> 2] for v in range(8)], float) * H
+    return (ijk * H)[:, None, :] + off[None, :, :]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower() == "active":
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arms (the ONLY places that touch oracle/): cpu_baseline sample and --impl reference
+# ------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+    lo, hi, g_ref, L = args
+    from oracle import msfec_oracle as mo
+    prob = mo.Problem(pairing="NED_RT", n_refine_local=L, n_refine_global=g_ref, random_field_seed=SEED,
+                      rhs_expr=RHS, rhs_constants={"scale": 100.0})
+    cells = morton_cells(g_ref, lo, hi)
+    acc = 0.0
+    for i in range(hi - lo):
+        M, r, *_ = mo.build_basis(prob, cells[i], lo + i)
+        acc += float(M[0, 0])
+    return acc
+
+
+def cpu_oracle_throughput(n_sample, g_ref, L, cores):
+    """cells/s of the oracle port (exact sparse direct solve per cell) on `cores` host processes."""
+    import multiprocessing as mp
+    per = max(1, n_sample // cores)
+    jobs = [(i * per, (i + 1) * per, g_ref, L) for i in range(cores)]
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_worker, [(0, 1, g_ref, L)] * cores)     # warm imports / topology caches
+        t0 = time.perf_counter()
+        pool.map(_oracle_worker, jobs)
+        dt = time.perf_counter() - t0
+    return per * cores / dt, per * cores, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--global-refinements", type=int, default=5)   # 32^3 coarse cells
+    ap.add_argument("--local-refinements", type=int, default=3)
+    ap.add_argument("--cells", type=int, default=0, help="use only the first C coarse cells (debug)")
+    ap.add_argument("--cells-per-batch", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="cells in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    g_ref, L = args.global_refinements, args.local_refinements
+    n_total = args.cells if args.cells else 8 ** g_ref
+    n_fine = 1944 + 1728 if L == 3 else None
+    k = 18
+    cores = os.cpu_count() or 1
+    workload = (f"synthetic 3D Ned_RT, rough random field (seed {SEED}, sigma ln(10)/2), "
+                f"{n_total} coarse cells (global refinements {g_ref}) x {L} local refinements")
+    config = {"workload": workload, "pairing": "NED_RT", "coarse_cells": n_total, "local_refinements": L,
+              "partition": f"contiguous Morton chunks over {world} rank(s)",
+              "cache": "inputs larger than L2 (per-step working set is GBs)"}
+
+    # ---------------- reference arm: the oracle port on the host cores --------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_sample = args.cpu_sample or 8 * cores
+        vals = []
+        for _ in range(args.warmup + args.steps):
+            v, n_done, dt = cpu_oracle_throughput(n_sample, g_ref, L, cores)
+            vals.append((v, dt))
+        v = float(np.mean([a for a, _ in vals[args.warmup:]]))
+        ms = float(np.mean([b for _, b in vals[args.warmup:]])) * 1e3
+        line = {"metric": "basis build throughput", "value": v, "unit": "coarse cells/s", "impl": "reference",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "coarse cells/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n_sample} cells of the same workload per step, oracle/msfec_oracle.py "
+                                           f"(exact SuperLU solve per cell), {cores} processes"},
+                "e2e": {"value": v, "unit": "coarse cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "fine_dof_solves_per_s": v * k * (n_fine or 0)}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm ------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    m = load_binding()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lo, hi = (rank * n_total) // world, ((rank + 1) * n_total) // world
+    n_loc = hi - lo
+    cells = morton_cells(g_ref, lo, hi)
+    ids = np.arange(lo, hi, dtype=np.int64)
+    prob = m.make_problem("NED_RT", n_refine_local=L, n_refine_global=g_ref, random_field_seed=SEED,
+                          rhs_expression=RHS, rhs_constants="scale=100", cells_per_batch=args.cells_per_batch)
+    bb = m.BasisBuilder(prob, device=local_rank)
+    dev = torch.device("cuda", local_rank)
+    # device-resident inputs/outputs for `value`; pinned host buffers for `e2e`
+    d_c = torch.tensor(cells, dtype=torch.float64, device=dev).contiguous()
+    d_i = torch.tensor(ids, dtype=torch.int64, device=dev)
+    d_M = torch.empty((n_loc, k, k), dtype=torch.float64, device=dev)
+    d_r = torch.empty((n_loc, k), dtype=torch.float64, device=dev)
+    h_c = torch.tensor(cells, dtype=torch.float64).pin_memory()
+    h_i = torch.tensor(ids, dtype=torch.int64).pin_memory()
+    h_M = torch.empty((n_loc, k, k), dtype=torch.float64).pin_memory()
+    h_r = torch.empty((n_loc, k), dtype=torch.float64).pin_memory()
+
+    def step_device():
+        bb.run_device(n_loc, d_c.data_ptr(), d_i.data_ptr(), d_M.data_ptr(), d_r.data_ptr())
+        return bb.stats
+
+    def step_e2e():
+        st = m.Stats()
+        rc = m.lib().msfec_build_basis(bb._ctx, n_loc, h_c.data_ptr(), h_i.data_ptr(), h_M.data_ptr(), h_r.data_ptr(),
+                                       m.C.byref(st))
+        if rc:
+            raise m.MsfecError(rc, m.lib().msfec_last_error(bb._ctx).decode())
+        return st.as_dict()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        stats = [fn() for _ in range(steps)]
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        barrier()
+        ev_ms = sum(s["ms_total"] for s in stats)          # CUDA events on the library's stream
+        t = torch.tensor([ev_ms, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), stats
+
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev_ms, wall_ms, stats = timed(step_device, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()                                             # warm the host path once
+    e_ev_ms, e_wall_ms, e_stats = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        ms_step = ev_ms / args.steps
+        value = n_total / (ms_step * 1e-3)
+        e2e_value = n_total / (e_wall_ms / args.steps * 1e-3)
+        st = stats[-1]
+        n_fine_dofs = st["n_fine_dofs"]
+        # roofline of the dominant kernel (k_minres_spmm): algorithmic bytes per launch:
+        # every per-cell matrix value of the interior system once per iteration + rhs/solution amortised.
+        launches = max(1, st["krylov_spmm_launches"])
+        bytes_per_launch = st["krylov_matrix_bytes"] / launches
+        spmm_ms = st["krylov_ms_spmm"]
+        peak, peak_src = hbm_peak()
+        achieved = bytes_per_launch / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+        line = {
+            "metric": "basis build throughput", "value": value, "unit": "coarse cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "fine_dof_solves_per_s": value * k * n_fine_dofs,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "coarse cells/s",
+                    "h2d_bytes_per_step": int(h_c.numel() * 8 + h_i.numel() * 8),
+                    "d2h_bytes_per_step": int(h_M.numel() * 8 + h_r.numel() * 8),
+                    "timing": "host wall clock around msfec_build_basis (pinned host buffers in, host buffers out), max over ranks"},
+            "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
+            "roofline": {"bound": "hbm", "kernel": "k_minres_spmm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": spmm_ms,
+                         "launches_per_step": int(launches)},
+            "phases_ms": {kk: st[kk] for kk in ("ms_assemble", "ms_lift", "ms_solve", "ms_gram")},
+            "krylov": {"iterations_max": st["iterations_max"], "iterations_mean": st["iterations_mean"],
+                       "residual_max": st["residual_max"], "not_converged": st["not_converged"]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            n_sample = args.cpu_sample or 8 * cores
+            v, n_done, dt = cpu_oracle_throughput(n_sample, g_ref, L, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "coarse cells/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_done} cells of the same workload in {dt:.1f} s, "
+                                              f"oracle/msfec_oracle.py (exact SuperLU solve per cell), {cores} processes"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -761,6 +761,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   alloc_store(n_cells);
   const int kg = T_.k_gram;
   // corners: bring to the device (host path) or use in place (device path); H from cell 0
+  CUDA_OK(cudaEventRecord(ev_[6], stream_));
   const double *dc = corners;
   const long long *dids = (const long long *)cell_ids;
   double c0[24];
@@ -786,7 +787,6 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   float ms_asm = 0, ms_lift = 0, ms_solve = 0, ms_gram = 0;
   double ms_spmm = 0;
   long total_it = 0;
-  CUDA_OK(cudaEventRecord(ev_[6], stream_));
   for (int cell0 = 0; cell0 < n_cells; cell0 += batch_cells) {
     const int nb = std::min(batch_cells, n_cells - cell0);
     const int groups = (nb + kLanes - 1) / kLanes;
