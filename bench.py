@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--local-refinements", type=int, default=3)
     ap.add_argument("--cells", type=int, default=0, help="use only the first C coarse cells (debug)")
     ap.add_argument("--cells-per-batch", type=int, default=0)
+    ap.add_argument("--solver", default="direct", choices=["direct", "minres"],
+                    help="'use direct solver basis' true (batched block LDL^T) / false (batched MINRES)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="cells in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -186,7 +188,8 @@ def main():
     cells = morton_cells(g_ref, lo, hi)
     ids = np.arange(lo, hi, dtype=np.int64)
     prob = m.make_problem("NED_RT", n_refine_local=L, n_refine_global=g_ref, random_field_seed=SEED,
-                          rhs_expression=RHS, rhs_constants="scale=100", cells_per_batch=args.cells_per_batch)
+                          rhs_expression=RHS, rhs_constants="scale=100", cells_per_batch=args.cells_per_batch,
+                          use_direct_solver_basis=1 if args.solver == "direct" else 0)
     bb = m.BasisBuilder(prob, device=local_rank)
     dev = torch.device("cuda", local_rank)
     # device-resident inputs/outputs for `value`; pinned host buffers for `e2e`

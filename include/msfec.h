@@ -90,6 +90,13 @@ typedef struct msfec_stats {
   double krylov_matrix_bytes;    /* algorithmic bytes of the Krylov kernel*/
   double krylov_ms_spmm;         /* device time inside the SpMM kernel               */
   int64_t krylov_spmm_launches;
+  /* direct path ("use direct solver basis = true") */
+  int64_t direct_update_launches;
+  double direct_flops;           /* FP64 flops of all trailing updates of the build (lower triangle) */
+  double direct_flops_timed;     /* flops of the update launches that were bracketed by events       */
+  double direct_ms_update;       /* summed device time of those launches                             */
+  int32_t solver;                /* 0 = batched MINRES, 1 = batched block LDL^T                       */
+  int32_t reserved2;
 } msfec_stats;
 
 typedef struct msfec_ctx msfec_ctx;

@@ -17,6 +17,7 @@ using namespace msfec;
 struct msfec_ctx {
   ProblemSpec spec;
   Topology topo;
+  DirectPlan plan;
   Engine *engine = nullptr;
   std::string last_error;
 };
@@ -203,7 +204,8 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
     ctx = new msfec_ctx();
     ctx->topo = build_topology(p->pairing, 1 << p->n_refine_local);
     make_spec(*p, ctx->topo, ctx->spec);
-    if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo);
+    ctx->plan = build_direct_plan(ctx->topo);
+    if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan);
     *out = ctx;
     return MSFEC_OK;
   } catch (const std::invalid_argument &e) {
@@ -303,6 +305,15 @@ int msfec_debug_table(const msfec_ctx *ctx, const char *name, void *out, size_t 
   };
   op_field("sys", t.sys); op_field("lift", t.lift); op_field("full", t.full); op_field("kint", t.kint);
   asm_field("asm00", t.asm00); asm_field("asm11", t.asm11); asm_field("asm_rhs", t.asm_rhs);
+  const DirectPlan &dp = ctx->plan;
+  std::vector<int32_t> col_off32;
+  if (n == "direct.perm") iv = &dp.perm; else if (n == "direct.inv_perm") iv = &dp.inv_perm;
+  else if (n == "direct.bs") iv = &dp.bs; else if (n == "direct.slab_off") iv = &dp.slab_off;
+  else if (n == "direct.ld") iv = &dp.ld; else if (n == "direct.cell_dest") iv = &dp.cell_dest;
+  else if (n == "direct.cell_ref") iv = &dp.cell_ref; else if (n == "direct.shared_dest") iv = &dp.shared_dest;
+  else if (n == "direct.shared_val") dv = &dp.shared_val; else if (n == "direct.const_dest") iv = &dp.const_dest;
+  else if (n == "direct.const_val") dv = &dp.const_val; else if (n == "direct.rhs_dest") iv = &dp.rhs_dest;
+  else if (n == "direct.col_off") { for (auto v : dp.col_off) col_off32.push_back((int32_t)v); iv = &col_off32; }
   if (n == "G") dv = &t.G; else if (n == "F1") dv = &t.F1;
   else if (n == "diag_slot0") iv = &t.diag_slot0; else if (n == "diag_slot1") iv = &t.diag_slot1;
   else if (n == "blk0.cell_dofs") iv = &t.blk[0].cell_dofs; else if (n == "blk1.cell_dofs") iv = &t.blk[1].cell_dofs;

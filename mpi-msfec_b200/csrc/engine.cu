@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -510,6 +511,12 @@ __global__ void k_prepare_cells(const double *__restrict__ corners, const long l
   gid[g * kLanes + lane] = ids ? ids[cell] : (long long)cell;
 }
 
+}  // namespace
+}  // namespace msfec
+#include "direct.cuh"
+namespace msfec {
+namespace {
+
 template <typename T>
 T *dev_upload(const std::vector<T> &h) {
   T *d = nullptr;
@@ -553,7 +560,8 @@ struct AsmStore {
 // ------------------------------------------------------------------------------------
 class Engine {
  public:
-  Engine(int device, const ProblemSpec &spec, const Topology &topo) : spec_(spec), T_(topo), device_(device) {
+  Engine(int device, const ProblemSpec &spec, const Topology &topo, const DirectPlan &plan)
+      : spec_(spec), T_(topo), P_(plan), device_(device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) throw std::runtime_error("no CUDA device available (there is no CPU fallback)");
@@ -570,16 +578,32 @@ class Engine {
     d_diag0_ = dev_upload(T_.diag_slot0); d_diag1_ = dev_upload(T_.diag_slot1);
     d_G_ = dev_upload(T_.G); d_F1_ = dev_upload(T_.F1);
     d_prog_ = dev_upload(spec_.programs);
-    CUDA_OK(cudaMalloc(&d_flag_, 2 * sizeof(int)));
-    CUDA_OK(cudaMallocHost(&h_flag_, 2 * sizeof(int)));
+    CUDA_OK(cudaMalloc(&d_flag_, 4 * sizeof(int)));
+    CUDA_OK(cudaMallocHost(&h_flag_, 4 * sizeof(int)));
     n_slots_ = T_.n_slots0 + T_.n_slots1;
+    use_direct_ = spec_.p.use_direct_solver_basis != 0;
+    if (const char *e = std::getenv("MSFEC_FORCE_SOLVER")) use_direct_ = std::string(e) == "direct";
+    if (use_direct_) {
+      d_dp_bs_ = dev_upload(P_.bs); d_dp_off_ = dev_upload(P_.slab_off); d_dp_ld_ = dev_upload(P_.ld);
+      std::vector<long long> co(P_.col_off.begin(), P_.col_off.end());
+      d_dp_col_ = dev_upload(co);
+      d_dp_inv_ = dev_upload(P_.inv_perm); d_dp_cdest_ = dev_upload(P_.cell_dest); d_dp_cref_ = dev_upload(P_.cell_ref);
+      d_dp_sdest_ = dev_upload(P_.shared_dest); d_dp_sval_ = dev_upload(P_.shared_val);
+      d_dp_kdest_ = dev_upload(P_.const_dest); d_dp_kval_ = dev_upload(P_.const_val); d_dp_rhs_ = dev_upload(P_.rhs_dest);
+      ev_upd_.resize(2048);
+      for (auto &ev : ev_upd_) CUDA_OK(cudaEventCreate(&ev));
+    }
     R_ = (T_.k_solve % 6 == 0) ? 6 : 4;
     if (T_.k_solve % R_) throw std::runtime_error("unsupported number of right-hand sides");
   }
 
   ~Engine() {
     cudaSetDevice(device_);
-    free_batch(); free_store();
+    free_batch(); free_store(); free_direct();
+    for (auto &ev : ev_upd_) cudaEventDestroy(ev);
+    cudaFree(d_dp_bs_); cudaFree(d_dp_off_); cudaFree(d_dp_ld_); cudaFree(d_dp_col_); cudaFree(d_dp_inv_);
+    cudaFree(d_dp_cdest_); cudaFree(d_dp_cref_); cudaFree(d_dp_sdest_); cudaFree(d_dp_sval_); cudaFree(d_dp_kdest_);
+    cudaFree(d_dp_kval_); cudaFree(d_dp_rhs_);
     sys_.release(); lift_.release(); full_.release(); kint_.release();
     asm00_.release(); asm11_.release(); asmrhs_.release();
     cudaFree(d_diag0_); cudaFree(d_diag1_); cudaFree(d_G_); cudaFree(d_F1_); cudaFree(d_prog_);
@@ -607,6 +631,7 @@ class Engine {
 
   ProblemSpec spec_;
   Topology T_;
+  DirectPlan P_;
   int device_;
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev_[8]{}, ev_sp_[2]{};
@@ -632,6 +657,21 @@ class Engine {
   bool have_weights_ = false;
   int last_batch_cell0_ = 0, last_batch_n_ = 0;
   long launches_ = 0;
+  // direct solver
+  bool use_direct_ = false;
+  int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
+  int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr;
+  long long *d_dp_col_ = nullptr;
+  int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
+      *d_dp_rhs_ = nullptr;
+  double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
+  double *d_band_ = nullptr, *d_diagL_ = nullptr, *d_dvec_ = nullptr, *d_xT_ = nullptr;
+  std::vector<cudaEvent_t> ev_upd_;
+  double direct_flops_ = 0, direct_ms_update_ = 0, direct_flops_timed_ = 0;
+  long direct_update_launches_ = 0;
+  void alloc_direct(int nb);
+  void free_direct();
+  void solve_direct_batch(int groups, int nb, double kscale, msfec_stats &st);
 };
 
 void Engine::free_batch() {
@@ -750,6 +790,87 @@ int Engine::solve_batch(int groups, int n_valid, double kscale, msfec_stats &st,
   return it;
 }
 
+
+void Engine::free_direct() {
+  cudaFree(d_band_); cudaFree(d_diagL_); cudaFree(d_dvec_); cudaFree(d_xT_);
+  d_band_ = d_diagL_ = d_dvec_ = d_xT_ = nullptr; direct_sub_ = 0;
+}
+
+void Engine::alloc_direct(int nb) {
+  // cells per sub-batch: bounded by a memory budget for the band (default 24 GB), multiple of 32
+  double budget_gb = 24.0;
+  if (const char *e = std::getenv("MSFEC_DIRECT_BAND_GB")) budget_gb = std::atof(e);
+  long sub = (long)(budget_gb * 1e9 / ((double)P_.band_doubles * 8.0));
+  if (const char *e = std::getenv("MSFEC_DIRECT_BATCH")) sub = std::atol(e);
+  sub = std::max(32L, sub / 32 * 32);
+  sub = std::min<long>(sub, (nb + 31) / 32 * 32);
+  sub = std::min<long>(sub, 65535 / 32 * 32);
+  if (sub <= direct_sub_) return;
+  free_direct();
+  CUDA_OK(cudaMalloc(&d_band_, (size_t)sub * P_.band_doubles * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_diagL_, (size_t)sub * P_.NP * kDP * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_dvec_, (size_t)sub * P_.NP * sizeof(double)));
+  CUDA_OK(cudaMalloc(&d_xT_, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
+  direct_sub_ = (int)sub;
+}
+
+void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &st) {
+  alloc_direct(nb);
+  const int k = T_.k_solve, NI = T_.NI, NP = P_.NP;
+  const size_t stride = (size_t)P_.band_doubles;
+  CUDA_OK(cudaMemsetAsync(d_vec_[7], 0, (size_t)groups * NI * k * kLanes * sizeof(double), stream_));
+  DirectPlanDev D{P_.n_slabs, NP, d_dp_bs_, d_dp_off_, d_dp_ld_, d_dp_col_};
+  bool timed = (direct_update_launches_ == 0);   // per-launch events on the first sub-batch of a build
+  for (int lo = 0; lo < nb; lo += direct_sub_) {
+    const int hi = std::min(nb, lo + direct_sub_), nc = hi - lo;
+    const int g0 = lo / kLanes, ng = (hi + kLanes - 1) / kLanes - g0;
+    CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
+    const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
+    k_direct_fill_cell<<<dim3((ne + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(ne, d_dp_cdest_, d_dp_cref_, d_vals_, n_slots_, g0, lo, hi, d_band_, stride);
+    if (nes) k_direct_fill_shared<<<dim3((nes + 255) / 256, nc), 256, 0, stream_>>>(nes, d_dp_sdest_, d_dp_sval_, kscale, d_band_, stride);
+    if (nek) k_direct_fill_shared<<<dim3((nek + 255) / 256, nc), 256, 0, stream_>>>(nek, d_dp_kdest_, d_dp_kval_, 1.0, d_band_, stride);
+    k_direct_fill_rhs<<<dim3((NI + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(NI, k, d_dp_rhs_, d_vec_[2], g0, lo, hi, d_band_, stride);
+    launches_ += 4;
+    size_t ev_i = 0;
+    std::vector<double> ev_flops;
+    for (int s = 0; s < P_.n_slabs; ++s) {
+      const int bs = P_.bs[s], ld = P_.ld[s];
+      const int bs_next = s + 1 < P_.n_slabs ? P_.bs[s + 1] : 0;
+      const long long co_next = s + 1 < P_.n_slabs ? P_.col_off[s + 1] : 0;
+      const int ld_next = s + 1 < P_.n_slabs ? P_.ld[s + 1] : 0;
+      const int rhs_row_next = ld_next - DirectPlan::kRhsRows;
+      for (int j0 = 0; j0 < bs; j0 += kDP) {
+        const int pglob = P_.slab_off[s] + j0;
+        const int nrows = ld - (j0 + kDP);
+        k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_, d_flag_ + 1 + 1);
+        ++launches_;
+        const int T = (nrows + 63) / 64;
+        const double R = nrows, Cn = bs + bs_next - (j0 + kDP);
+        const double flops = Cn > 0 ? 2.0 * kDP * (Cn * R - Cn * (Cn - 1) / 2.0) * nc : 0.0;
+        direct_flops_ += flops;
+        const bool tev = timed && ev_i + 2 <= ev_upd_.size();
+        if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
+        k_direct_update<<<dim3(T, T, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, j0, pglob, NP, d_dvec_);
+        if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
+        ++launches_; ++direct_update_launches_;
+      }
+    }
+    k_direct_backward<<<nc, 256, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);
+    k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
+    launches_ += 2;
+    if (timed) {
+      CUDA_OK(cudaStreamSynchronize(stream_));
+      for (size_t i = 0; i + 1 < ev_i + 1 && i / 2 < ev_flops.size(); i += 2) {
+        float ms = 0;
+        CUDA_OK(cudaEventElapsedTime(&ms, ev_upd_[i], ev_upd_[i + 1]));
+        direct_ms_update_ += ms; direct_flops_timed_ += ev_flops[i / 2];
+      }
+      timed = false;
+    }
+  }
+  (void)st;
+}
+
 int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix, double *elem_rhs,
                   bool device_ptrs, msfec_stats *stats) {
   CUDA_OK(cudaSetDevice(device_));
@@ -757,6 +878,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   msfec_stats st{};
   st.n_cells = n_cells; st.k = T_.k_gram; st.n_fine_dofs = T_.NF; st.n_fine_dofs_interior = T_.NI;
   launches_ = 0; spmm_samples_ = 0; cell_iters_ = 0;
+  direct_flops_ = direct_ms_update_ = direct_flops_timed_ = 0; direct_update_launches_ = 0;
   have_weights_ = false;
   alloc_store(n_cells);
   const int kg = T_.k_gram;
@@ -783,7 +905,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   const int cpb = spec_.p.cells_per_batch > 0 ? spec_.p.cells_per_batch : 4096;
   const int batch_cells = std::min(n_cells, (cpb + kLanes - 1) / kLanes * kLanes);
   alloc_batch((batch_cells + kLanes - 1) / kLanes);
-  CUDA_OK(cudaMemsetAsync(d_flag_, 0, 2 * sizeof(int), stream_));
+  CUDA_OK(cudaMemsetAsync(d_flag_, 0, 4 * sizeof(int), stream_));
   float ms_asm = 0, ms_lift = 0, ms_solve = 0, ms_gram = 0;
   double ms_spmm = 0;
   long total_it = 0;
@@ -811,7 +933,8 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
         lift_.dev, T_.NI, T_.NB, T_.k_solve, n_slots_, kscale, f1scale, d_vals_, d_G_, d_F1_, d_vec_[2]);
     launches_ += 3;
     CUDA_OK(cudaEventRecord(ev_[2], stream_));
-    { const int itb = solve_batch(groups, nb, kscale, st, ms_spmm); total_it += itb; cell_iters_ += (double)itb * nb; }
+    if (use_direct_) solve_direct_batch(groups, nb, kscale, st);
+    else { const int itb = solve_batch(groups, nb, kscale, st, ms_spmm); total_it += itb; cell_iters_ += (double)itb * nb; }
     CUDA_OK(cudaEventRecord(ev_[3], stream_));
     const int gz0 = cell0 / kLanes;
     BasisDims D{T_.blk[0].n_int, T_.two_blocks ? T_.blk[1].n_int : 0, T_.blk[0].n_total,
@@ -838,12 +961,13 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     CUDA_OK(cudaMemcpyAsync(elem_matrix, d_M_, (size_t)n_cells * kg * kg * sizeof(double), cudaMemcpyDeviceToHost, stream_));
     CUDA_OK(cudaMemcpyAsync(elem_rhs, d_r_, (size_t)n_cells * kg * sizeof(double), cudaMemcpyDeviceToHost, stream_));
   }
-  CUDA_OK(cudaMemcpyAsync(h_flag_, d_flag_, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaMemcpyAsync(h_flag_, d_flag_, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream_));
   CUDA_OK(cudaEventRecord(ev_[7], stream_));
   CUDA_OK(cudaStreamSynchronize(stream_));
   CUDA_OK(cudaGetLastError());
   if (h_flag_[1]) throw std::invalid_argument("coarse cell " + std::to_string(h_flag_[1] - 1) +
                                               " is not an axis-aligned cube of the common edge length");
+  if (h_flag_[2]) st.not_converged += 1;   // zero / non-finite pivot in the direct factorisation
   float ms_total;
   CUDA_OK(cudaEventElapsedTime(&ms_total, ev_[6], ev_[7]));
   st.iterations_mean /= std::max<double>(1.0, (double)n_cells * T_.k_solve);
@@ -854,6 +978,8 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   st.krylov_matrix_bytes = 8.0 * (double)T_.sys.cref.size() * cell_iters_ + 2.0 * 8.0 * T_.k_solve * (double)T_.NI * n_cells;
   st.krylov_spmm_launches = total_it;
   st.krylov_ms_spmm = spmm_samples_ ? ms_spmm / spmm_samples_ : 0.0;   // mean duration of one SpMM launch
+  st.direct_flops = direct_flops_; st.direct_flops_timed = direct_flops_timed_; st.direct_ms_update = direct_ms_update_;
+  st.direct_update_launches = direct_update_launches_; st.solver = use_direct_ ? 1 : 0;
   if (stats) *stats = st;
   return st.not_converged ? MSFEC_ENOTCONVERGED : MSFEC_OK;
 }
@@ -909,7 +1035,9 @@ void Engine::cell_values(int cell, double *values, size_t *count) {
 }
 
 // ------------------------------------------------------------------------------------
-Engine *engine_create(int device, const ProblemSpec &spec, const Topology &topo) { return new Engine(device, spec, topo); }
+Engine *engine_create(int device, const ProblemSpec &spec, const Topology &topo, const DirectPlan &plan) {
+  return new Engine(device, spec, topo, plan);
+}
 void engine_destroy(Engine *e) { delete e; }
 
 #define GUARD(body)                                                                \

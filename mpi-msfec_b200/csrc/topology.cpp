@@ -480,3 +480,87 @@ Topology build_topology(int pairing, int n) {
 }
 
 }  // namespace msfec
+
+namespace msfec {
+
+DirectPlan build_direct_plan(const Topology &t) {
+  DirectPlan P;
+  const int n = t.n, NI0 = t.blk[0].n_int;
+  const int NI1 = t.two_blocks ? t.blk[1].n_int : 0;
+  constexpr int PW = DirectPlan::kPanel;
+  auto slab_of = [&](int blk, int dof) {
+    const double z = t.blk[blk].pos[3 * dof + 2];
+    int s = (int)std::ceil(z) - 1;
+    return std::min(std::max(s, 0), n - 1);
+  };
+  // members of each slab: sigma-type first, then u-type (interior DoFs only)
+  std::vector<std::vector<int>> members(n);   // stacked interior row index
+  for (int d = 0; d < NI0; ++d) members[slab_of(0, d)].push_back(d);
+  for (int d = 0; d < NI1; ++d) members[slab_of(1, d)].push_back(NI0 + d);
+  // RT_DQ: the system has the constant-u null space (rt_dq_basis.cc:683-709); fix the last
+  // u DoF of the last slab to zero.  sigma is unaffected, u is overwritten by 1 afterwards.
+  if (t.pairing == MSFEC_RT_DQ) P.pinned_row = members[n - 1].back();
+  // drop empty slabs (Q: slab n-1 holds no interior vertex)
+  std::vector<std::vector<int>> slabs;
+  for (auto &m : members) if (!m.empty()) slabs.push_back(m);
+  P.n_slabs = (int)slabs.size();
+  P.bs.resize(P.n_slabs); P.slab_off.resize(P.n_slabs); P.ld.resize(P.n_slabs); P.col_off.resize(P.n_slabs);
+  int off = 0;
+  for (int s = 0; s < P.n_slabs; ++s) {
+    P.bs[s] = ((int)slabs[s].size() + PW - 1) / PW * PW;
+    P.slab_off[s] = off;
+    off += P.bs[s];
+  }
+  P.NP = off;
+  int64_t boff = 0;
+  for (int s = 0; s < P.n_slabs; ++s) {
+    P.ld[s] = P.bs[s] + (s + 1 < P.n_slabs ? P.bs[s + 1] : 0) + DirectPlan::kRhsRows;
+    P.col_off[s] = boff;
+    boff += (int64_t)P.ld[s] * P.bs[s];
+  }
+  P.band_doubles = boff;
+  if (boff >= (int64_t)1 << 31) throw std::runtime_error("direct solver band exceeds 2^31 entries per cell");
+  P.perm.assign(t.NI, -1); P.inv_perm.assign(P.NP, -1);
+  std::vector<int> slab_of_p(P.NP, 0);
+  for (int s = 0; s < P.n_slabs; ++s) {
+    for (int i = 0; i < (int)slabs[s].size(); ++i) {
+      P.perm[slabs[s][i]] = P.slab_off[s] + i;
+      P.inv_perm[P.slab_off[s] + i] = slabs[s][i];
+    }
+    for (int i = 0; i < P.bs[s]; ++i) slab_of_p[P.slab_off[s] + i] = s;
+  }
+  auto dest_of = [&](int pr, int pc) -> int64_t {   // lower entry (pr >= pc)
+    const int s = slab_of_p[pc];
+    if (slab_of_p[pr] != s && slab_of_p[pr] != s + 1) throw std::runtime_error("direct plan: matrix is not block tridiagonal");
+    return P.col_off[s] + (int64_t)(pc - P.slab_off[s]) * P.ld[s] + (pr - P.slab_off[s]);
+  };
+  const RefOperator &S = t.sys;
+  for (int r = 0; r < S.n_rows; ++r) {
+    const int pr = P.perm[r];
+    for (int e = S.cptr[r]; e < S.cptr[r + 1]; ++e) {
+      const int c = S.ccol[e], pc = P.perm[c];
+      if (pr < pc || r == P.pinned_row || c == P.pinned_row) continue;
+      P.cell_dest.push_back((int32_t)dest_of(pr, pc)); P.cell_ref.push_back(S.cref[e]);
+    }
+    for (int e = S.sptr[r]; e < S.sptr[r + 1]; ++e) {
+      const int c = S.scol[e], pc = P.perm[c];
+      if (pr < pc || r == P.pinned_row || c == P.pinned_row) continue;
+      P.shared_dest.push_back((int32_t)dest_of(pr, pc)); P.shared_val.push_back(S.sval[e]);
+    }
+  }
+  for (int p = 0; p < P.NP; ++p) {
+    const int r = P.inv_perm[p];
+    if (r < 0) { P.const_dest.push_back((int32_t)dest_of(p, p)); P.const_val.push_back(1.0); }
+    else if (r == P.pinned_row) { P.const_dest.push_back((int32_t)dest_of(p, p)); P.const_val.push_back(-1.0); }
+  }
+  P.rhs_dest.assign(t.NI, -1);
+  for (int r = 0; r < t.NI; ++r) {
+    if (r == P.pinned_row) continue;
+    const int p = P.perm[r], s = slab_of_p[p];
+    P.rhs_dest[r] = (int32_t)(P.col_off[s] + (int64_t)(p - P.slab_off[s]) * P.ld[s] + (P.ld[s] - DirectPlan::kRhsRows));
+  }
+  if (P.pinned_row >= 0) P.inv_perm[P.perm[P.pinned_row]] = -1;   // solution there stays 0
+  return P;
+}
+
+}  // namespace msfec

@@ -22,17 +22,20 @@ def _check_cells(bb, prob, cells, ids, which):
     return worst
 
 
+@pytest.mark.parametrize("direct", [0, 1], ids=["minres", "direct"])
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
 @pytest.mark.parametrize("L", [2, 3])
-def test_prm_coefficients_match_oracle(msfec, pairing, L):
-    """configs[0..3] coefficients (examples/prm == reference test-01 files) on the 64-cell coarse mesh."""
+def test_prm_coefficients_match_oracle(msfec, pairing, L, direct):
+    """configs[0..3] coefficients (examples/prm == reference test-01 files) on the 64-cell coarse mesh,
+    through both solver paths of the reference: `use direct solver basis` false (batched MINRES) / true
+    (batched block LDL^T)."""
     cells = mo.morton_cells(2)
     ids = np.arange(64)
-    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L), device=0).run(cells, ids)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, use_direct_solver_basis=direct), device=0).run(cells, ids)
     worst = _check_cells(bb, oracle_problem(pairing, L), cells, ids, (0, 21, 37, 63))
     print(pairing, L, "worst", worst, bb.stats)
     assert worst < TOL
-    assert bb.stats["not_converged"] == 0 and bb.stats["kernel_launches"] > 0
+    assert bb.stats["not_converged"] == 0 and bb.stats["kernel_launches"] > 0 and bb.stats["solver"] == direct
 
 
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
@@ -46,11 +49,12 @@ def test_golden_fixtures(msfec, pairing):
         assert np.abs(bb.get_global_element_rhs()[c] - ro).max() <= TOL * max(np.abs(ro).max(), 1e-300)
 
 
-def test_random_field_ragged_batches(msfec):
+@pytest.mark.parametrize("direct", [0, 1], ids=["minres", "direct"])
+def test_random_field_ragged_batches(msfec, direct):
     """C5-style rough field; 70 cells = 2 full lane groups + a ragged one, split over 2 batches."""
     cells = mo.morton_cells(3)[100:170]
     ids = np.arange(100, 170)
-    p = lib_problem(msfec, "NED_RT", 2, random_seed=20261017, cells_per_batch=64)
+    p = lib_problem(msfec, "NED_RT", 2, random_seed=20261017, cells_per_batch=64, use_direct_solver_basis=direct)
     bb = msfec.BasisBuilder(p, device=0).run(cells, ids)
     worst = _check_cells(bb, oracle_problem("NED_RT", 2, random_seed=20261017), cells, ids, (0, 31, 32, 63, 64, 69))
     assert worst < TOL
@@ -88,7 +92,7 @@ def test_constant_coefficient_reproduction_on_gpu(msfec):
     for pairing in mo.PAIRINGS:
         rhs = b"1;2;3" if pairing in ("Q_NED", "NED_RT") else b"1"
         p = msfec.make_problem(pairing, n_refine_local=3, a_rotate=0, a_scale=(2.0, 3.0, 0.5), a_freq=(0, 0, 0),
-                               b_expression=b"1.7", rhs_expression=rhs)
+                               b_expression=b"1.7", rhs_expression=rhs, use_direct_solver_basis=1)
         bb = msfec.BasisBuilder(p, device=0).run(cells)
         prob0 = mo.Problem(pairing=pairing, n_refine_local=0, a_freq=(0, 0, 0), a_scale=(2.0, 3.0, 0.5),
                            a_rotate=False, b_expr="1.7", rhs_expr=rhs.decode())
@@ -97,10 +101,11 @@ def test_constant_coefficient_reproduction_on_gpu(msfec):
             assert rel_err(bb.get_global_element_matrix()[c], M0) < TOL
 
 
-def test_structure_properties_at_scale(msfec):
+@pytest.mark.parametrize("direct", [0, 1], ids=["minres", "direct"])
+def test_structure_properties_at_scale(msfec, direct):
     """Size-independent properties on 1024 random-field cells (no oracle solve needed)."""
     cells = mo.morton_cells(4)[:1024]
-    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017)
+    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017, use_direct_solver_basis=direct)
     bb = msfec.BasisBuilder(p, device=0).run(cells)
     M = bb.get_global_element_matrix()
     s = np.abs(M).max(axis=(1, 2))

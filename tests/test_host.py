@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol(msfec):
 def test_struct_layout_matches_header(msfec):
     # sizeof checks guard the ctypes mirror against drift
     assert C.sizeof(msfec.Problem) == 4 * 6 + 4 * 3 + 4 + 8 * 3 * 2 + 8 * 2 + 8 * 3 + 8 + 8 + 8 + 4 + 4
-    assert C.sizeof(msfec.Stats) == 4 * 8 + 8 * 9 + 8
+    assert C.sizeof(msfec.Stats) == 4 * 8 + 8 * 9 + 8 + 8 + 8 * 3 + 4 + 4
 
 
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
