@@ -57,52 +57,74 @@ __global__ void k_direct_fill_rhs(int NI, int k, const int *__restrict__ rhs_des
 }
 
 // ---- panel factorisation ---------------------------------------------------------------
-// grid (ceil(nrows/128), cells), block 128.  Virtual rows v in [j0+32, ld) are solved against the
-// diagonal block at (j0, j0).  Every CTA factors the (read-only) diagonal block redundantly in
-// shared memory; CTA x==0 publishes it to diagL / dvec.
+// LDL^T of a 32x32 block held one row per lane (registers + shuffles, no shared-memory
+// round trips).  On return lane i holds row i of the unit-lower factor in a[0..i-1] and the
+// pivot d_i in a[i]; the function returns d_lane.
+__device__ __forceinline__ double ldl32_rows(double (&a)[kDP], int lane, int *bad) {
+  double my_d = 0.0;
+#pragma unroll
+  for (int p = 0; p < kDP; ++p) {
+    const double ap = a[p];                                  // unscaled column p, one entry per lane
+    const double d = __shfl_sync(0xffffffffu, ap, p);
+    const double dinv = 1.0 / d;
+    const double l = ap * dinv;
+    if (lane == p) {
+      my_d = d;
+      if (!(fabs(d) > 1e-300) || !isfinite(d)) atomicExch(bad, 1);
+    }
+#pragma unroll
+    for (int j = p + 1; j < kDP; ++j) {
+      const double ajp = __shfl_sync(0xffffffffu, ap, j);
+      if (j <= lane) a[j] = fma(-l, ajp, a[j]);
+    }
+    if (lane > p) a[p] = l;
+  }
+  return my_d;
+}
+
+// Factor the 32x32 diagonal block at (j0, j0) of every cell: one warp per cell, publishes the unit-lower
+// factor (column-major, pivots on the diagonal) to diagL and the pivots to dvec.
+// grid (ceil(cells/4)), block 128
+__global__ void __launch_bounds__(128)
+k_direct_diag(const double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int pglob, int NP,
+              int n_cells, double *__restrict__ diagL, double *__restrict__ dvec, int *__restrict__ bad) {
+  const int cell = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (cell >= n_cells) return;
+  const double *P = band + (size_t)cell * band_stride + col_off;
+  double a[kDP];
+#pragma unroll
+  for (int p = 0; p < kDP; ++p) a[p] = (p <= lane) ? P[(size_t)(j0 + p) * ld + j0 + lane] : 0.0;
+  const double di = ldl32_rows(a, lane, bad);
+  double *dl = diagL + ((size_t)cell * NP + pglob) * kDP;
+#pragma unroll
+  for (int p = 0; p < kDP; ++p) dl[(size_t)p * kDP + lane] = a[p];
+  dvec[(size_t)cell * NP + pglob + lane] = di;
+}
+
+// Row-parallel triangular solve of the virtual rows v in [j0+32, ld) (rest of slab s, slab s+1 and the rhs
+// rows: forward substitution is fused into the factorisation) against the factored diagonal block.
+// grid (ceil(nrows/128), cells), block 128
 __global__ void __launch_bounds__(128)
 k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int pglob, int NP,
-               double *__restrict__ diagL, double *__restrict__ dvec, int *__restrict__ bad) {
+               const double *__restrict__ diagL, const double *__restrict__ dvec) {
   __shared__ double Ld[kDP][kDP + 1];
   __shared__ double dinv[kDP];
   const int cell = blockIdx.y, tid = threadIdx.x;
   double *P = band + (size_t)cell * band_stride + col_off;
+  const int v = j0 + kDP + blockIdx.x * 128 + tid;
+  double y[kDP];
+  if (v < ld) {
+#pragma unroll
+    for (int p = 0; p < kDP; ++p) y[p] = P[(size_t)(j0 + p) * ld + v];
+  }
+  const double *dl = diagL + ((size_t)cell * NP + pglob) * kDP;
   for (int idx = tid; idx < kDP * kDP; idx += 128) {
     const int i = idx & 31, p = idx >> 5;
-    Ld[i][p] = (i >= p) ? P[(size_t)(j0 + p) * ld + j0 + i] : 0.0;
+    Ld[i][p] = dl[(size_t)p * kDP + i];
   }
+  if (tid < kDP) dinv[tid] = 1.0 / dvec[(size_t)cell * NP + pglob + tid];
   __syncthreads();
-  if (tid < 32) {
-    const int i = tid;
-    for (int p = 0; p < kDP; ++p) {
-      const double d = Ld[p][p];
-      const double l = Ld[i][p] / d;
-      __syncwarp();
-      if (i > p)
-        for (int j = p + 1; j <= i; ++j) Ld[i][j] -= l * Ld[j][p];
-      __syncwarp();
-      if (i > p) Ld[i][p] = l;
-      if (i == p) {
-        dinv[p] = 1.0 / d;
-        if (!(fabs(d) > 1e-300) || !isfinite(d)) atomicExch(bad, 1);
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0) {
-    double *dl = diagL + ((size_t)cell * NP + pglob) * kDP;
-    for (int idx = tid; idx < kDP * kDP; idx += 128) {
-      const int i = idx & 31, p = idx >> 5;
-      dl[(size_t)p * kDP + i] = Ld[i][p];          // column p of the unit-lower factor (diag holds d_p)
-    }
-    if (tid < kDP) dvec[(size_t)cell * NP + pglob + tid] = Ld[tid][tid];
-  }
-  const int v = j0 + kDP + blockIdx.x * 128 + tid;
   if (v >= ld) return;
-  double y[kDP];
-#pragma unroll
-  for (int p = 0; p < kDP; ++p) y[p] = P[(size_t)(j0 + p) * ld + v];
 #pragma unroll
   for (int p = 1; p < kDP; ++p) {
     double s = y[p];
@@ -119,72 +141,112 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kLDT = 72;   // shared-memory stride (doubles) of one panel column: 64 rows + 8 pad
+constexpr size_t kUpdateSmem = (3 * kDP * kLDT + kDP) * sizeof(double);
+
+// stage a 64-row x 32-column block of the panel (global: column-major, rows contiguous) into
+// shared memory [p][i]; rows >= ld are zero-filled.  128 threads, 8 x 16-byte chunks each.
+__device__ __forceinline__ void stage_block(double *dst, const double *P, int ld, int j0, int row0, int tid) {
+#pragma unroll
+  for (int t = 0; t < 8; ++t) {
+    const int chunk = tid + t * 128;        // 0..1023
+    const int p = chunk >> 5, i = (chunk & 31) * 2;
+    double *d = dst + p * kLDT + i;
+    if (row0 + i < ld) cp_async16(d, P + (size_t)(j0 + p) * ld + row0 + i);
+    else { d[0] = 0.0; d[1] = 0.0; }
+  }
+}
 
 // C(vr, vc) -= sum_p L(vr, p) d_p L(vc, p) over the trailing region vr >= vc >= j0+32 of block
 // column s (virtual index space [slab s | slab s+1 | rhs rows]); targets in columns >= bs live in
-// block column s+1.  grid (T, T, cells) with T = ceil((ld - j0 - 32) / 64); block 128 (2x2 warps).
+// block column s+1.  grid (Tc, cells): one CTA per 64-wide column strip; it keeps the (scaled on
+// the fly) column operand in shared memory and walks down the row tiles with a cp.async double
+// buffer; the C tile is loaded straight into the DMMA accumulators.  block 128 = 2x2 warps of
+// 32x32.
 __global__ void __launch_bounds__(128)
 k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int bs, int bs_next,
                 long long col_off_next, int ld_next, int rhs_row_next, int j0, int pglob, int NP,
                 const double *__restrict__ dvec) {
-  const int ti = blockIdx.x, tj = blockIdx.y;
-  if (tj > ti) return;
-  constexpr int LDS = kDP + 4;   // padded row stride (doubles)
-  __shared__ double Lr[64][LDS];
-  __shared__ double Lc[64][LDS];
-  const int cell = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  extern __shared__ __align__(16) double upd_smem[];
+  double *Lc = upd_smem;
+  double (*Lr)[kDP * kLDT] = reinterpret_cast<double (*)[kDP * kLDT]>(upd_smem + kDP * kLDT);
+  double *dsm = upd_smem + 3 * kDP * kLDT;
+  const int tj = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v0 = j0 + kDP;
+  const int cbase = v0 + tj * 64;
+  const int T = (ld - v0 + 63) / 64;
   double *cb = band + (size_t)cell * band_stride;
   const double *P = cb + col_off;
-  const int v0 = j0 + kDP;
-  const int rbase = v0 + ti * 64, cbase = v0 + tj * 64;
-  const double *dv = dvec + (size_t)cell * NP + pglob;
-  // stage the two 64 x 32 operand blocks (column-major in global: contiguous along rows)
-  for (int idx = tid; idx < 64 * kDP; idx += 128) {
-    const int i = idx & 63, p = idx >> 6;
-    const int vr = rbase + i, vc = cbase + i;
-    Lr[i][p] = vr < ld ? P[(size_t)(j0 + p) * ld + vr] : 0.0;
-    Lc[i][p] = vc < ld ? P[(size_t)(j0 + p) * ld + vc] * dv[p] : 0.0;
-  }
-  __syncthreads();
+  if (tid < kDP) dsm[tid] = dvec[(size_t)cell * NP + pglob + tid];
+  stage_block(Lc, P, ld, j0, cbase, tid);
+  stage_block(Lr[0], P, ld, j0, cbase, tid);
+  cp_async_commit();
   const int wr = warp >> 1, wc = warp & 1;
-  const int vr0 = rbase + wr * 32, vc0 = cbase + wc * 32;
-  if (vr0 < vc0 || vr0 >= ld || vc0 >= bs + bs_next) return;
-  double acc[4][4][2];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
   const int fr = lane >> 2, fk = lane & 3;
-#pragma unroll
-  for (int ks = 0; ks < kDP / 4; ++ks) {
-    double af[4], bf[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      af[t] = Lr[wr * 32 + t * 8 + fr][ks * 4 + fk];
-      bf[t] = Lc[wc * 32 + t * 8 + fr][ks * 4 + fk];
-    }
-#pragma unroll
-    for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
-  }
-  // destination mapping of this warp's 32x32 sub-block (uniform per warp; all bounds are multiples of 32)
+  const int vc0 = cbase + wc * 32;
+  const bool col_ok = vc0 < bs + bs_next;
+  // destination columns of this warp (uniform): block column s or s+1
   double *cdst;
-  int ldc, roff;
-  if (vc0 < bs) { cdst = cb + col_off + (size_t)vc0 * ld; ldc = ld; roff = vr0; }
-  else {
-    cdst = cb + col_off_next + (size_t)(vc0 - bs) * ld_next; ldc = ld_next;
-    roff = vr0 < bs + bs_next ? vr0 - bs : rhs_row_next + (vr0 - bs - bs_next);
-  }
+  int ldc;
+  if (vc0 < bs) { cdst = cb + col_off + (size_t)vc0 * ld; ldc = ld; }
+  else { cdst = cb + col_off_next + (size_t)(vc0 - bs) * ld_next; ldc = ld_next; }
+  for (int ti = tj; ti < T; ++ti) {
+    const int buf = (ti - tj) & 1;
+    const int rbase = v0 + ti * 64;
+    if (ti + 1 < T) stage_block(Lr[buf ^ 1], P, ld, j0, rbase + 64, tid);
+    cp_async_commit();
+    const int vr0 = rbase + wr * 32;
+    const bool active = col_ok && vr0 >= vc0 && vr0 < ld;
+    int roff = vr0;
+    if (vc0 >= bs) roff = vr0 < bs + bs_next ? vr0 - bs : rhs_row_next + (vr0 - bs - bs_next);
+    double acc[4][4][2];
+    if (active) {
 #pragma unroll
-  for (int mt = 0; mt < 4; ++mt)
+      for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        double *p = cdst + (size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr;
-        *p -= acc[mt][nt][h];
+          for (int h = 0; h < 2; ++h)
+            acc[mt][nt][h] = cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr];
+    }
+    cp_async_wait<1>();
+    __syncthreads();
+    if (active) {
+      const double *A = Lr[buf] + wr * 32 + fr;
+      const double *B = Lc + wc * 32 + fr;
+#pragma unroll
+      for (int ks = 0; ks < kDP / 4; ++ks) {
+        const int kk = ks * 4 + fk;
+        const double dk = dsm[kk];
+        double af[4], bf[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          af[t] = -A[kk * kLDT + t * 8];
+          bf[t] = B[kk * kLDT + t * 8] * dk;
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr] = acc[mt][nt][h];
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
 }
 
 // ---- backward substitution -------------------------------------------------------------
@@ -195,10 +257,15 @@ struct DirectPlanDev {
 };
 
 // L^T x = z.  One CTA (256 threads) per cell; xT[cell][j][NP] is both output and the running
-// solution read by later (lower-numbered) panels.
-__global__ void __launch_bounds__(256)
+// solution read by later (lower-numbered) panels.  Per panel: (1) t = z - L(below)^T x with the
+// L rows staged through shared memory (lane = panel column, warp w owns rhs w, w+8, w+16), (2)
+// unit upper-triangular solve with the diagonal block, one thread per rhs, column oriented.
+__global__ void __launch_bounds__(256, 3)
 k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, const double *__restrict__ diagL,
                   int k, double *xT) {
+  constexpr int CH = 64;
+  __shared__ double Ls[CH][kDP + 1];
+  __shared__ double xs[CH][kMaxK + 1];
   __shared__ double tt[kDP][kMaxK + 1];
   __shared__ double Ld[kDP][kDP + 1];
   const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -209,28 +276,31 @@ k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPla
     const int rows_dof = ld - DirectPlan::kRhsRows, rhs_row = rows_dof;
     const double *P = band + (size_t)cell * band_stride + D.col_off[s];
     for (int j0 = bs - kDP; j0 >= 0; j0 -= kDP) {
-      // phase 1: t_c = z_c - sum_{i >= j0+32} L(i, c) x_i   (warp w: columns j0 + 4w .. 4w+3)
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = j0 + warp * 4 + cc;
-        const double *col = P + (size_t)c * ld;
-        double acc[kMaxK];
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int r0 = j0 + kDP; r0 < rows_dof; r0 += CH) {
+        {   // stage CH rows x 32 columns of L and CH rows x k of x
+          const int i = tid & (CH - 1), cg = tid >> 6;
+          const bool ok = r0 + i < rows_dof;
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j) acc[j] = 0.0;
-        for (int i = j0 + kDP + lane; i < rows_dof; i += 32) {
-          const double l = col[i];
-#pragma unroll
-          for (int j = 0; j < kMaxK; ++j)
-            if (j < k) acc[j] = fma(l, x[(size_t)j * NP + so + i], acc[j]);
+          for (int q = 0; q < 8; ++q) Ls[i][cg * 8 + q] = ok ? P[(size_t)(j0 + cg * 8 + q) * ld + r0 + i] : 0.0;
+          for (int j = cg; j < k; j += 4) xs[i][j] = ok ? x[(size_t)j * NP + so + r0 + i] : 0.0;
         }
+        __syncthreads();
+#pragma unroll 8
+        for (int i = 0; i < CH; ++i) {
+          const double l = Ls[i][lane];
 #pragma unroll
-        for (int j = 0; j < kMaxK; ++j) {
-          if (j < k) {
-            double a = acc[j];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (lane == j) tt[warp * 4 + cc][j] = col[rhs_row + j] - a;
+          for (int jj = 0; jj < 3; ++jj) {
+            const int j = warp + 8 * jj;
+            if (j < k) acc[jj] = fma(l, xs[i][j], acc[jj]);
           }
         }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int jj = 0; jj < 3; ++jj) {
+        const int j = warp + 8 * jj;
+        if (j < k) tt[lane][j] = P[(size_t)(j0 + lane) * ld + rhs_row + j] - acc[jj];
       }
       const double *dl = diagL + ((size_t)cell * NP + so + j0) * kDP;
       for (int idx = tid; idx < kDP * kDP; idx += 256) {
@@ -238,18 +308,18 @@ k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPla
         Ld[i][p] = dl[(size_t)p * kDP + i];
       }
       __syncthreads();
-      // phase 2: unit upper-triangular solve with the diagonal block, one thread per rhs
       if (tid < k) {
-        double xs[kDP];
+        double t[kDP];
+#pragma unroll
+        for (int c = 0; c < kDP; ++c) t[c] = tt[c][tid];
 #pragma unroll
         for (int c = kDP - 1; c >= 0; --c) {
-          double v = tt[c][tid];
+          const double xc = t[c];
 #pragma unroll
-          for (int i = c + 1; i < kDP; ++i) v = fma(-Ld[i][c], xs[i], v);
-          xs[c] = v;
+          for (int i = 0; i < c; ++i) t[i] = fma(-Ld[c][i], xc, t[i]);
         }
 #pragma unroll
-        for (int c = 0; c < kDP; ++c) x[(size_t)tid * NP + so + j0 + c] = xs[c];
+        for (int c = 0; c < kDP; ++c) x[(size_t)tid * NP + so + j0 + c] = t[c];
       }
       __syncthreads();
     }

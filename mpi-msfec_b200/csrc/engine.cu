@@ -590,6 +590,7 @@ class Engine {
       d_dp_inv_ = dev_upload(P_.inv_perm); d_dp_cdest_ = dev_upload(P_.cell_dest); d_dp_cref_ = dev_upload(P_.cell_ref);
       d_dp_sdest_ = dev_upload(P_.shared_dest); d_dp_sval_ = dev_upload(P_.shared_val);
       d_dp_kdest_ = dev_upload(P_.const_dest); d_dp_kval_ = dev_upload(P_.const_val); d_dp_rhs_ = dev_upload(P_.rhs_dest);
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem));
       ev_upd_.resize(2048);
       for (auto &ev : ev_upd_) CUDA_OK(cudaEventCreate(&ev));
     }
@@ -842,15 +843,16 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       for (int j0 = 0; j0 < bs; j0 += kDP) {
         const int pglob = P_.slab_off[s] + j0;
         const int nrows = ld - (j0 + kDP);
-        k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_, d_flag_ + 1 + 1);
-        ++launches_;
-        const int T = (nrows + 63) / 64;
+        k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_flag_ + 2);
+        k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_);
+        launches_ += 2;
+        const int Tc = (bs + bs_next - (j0 + kDP) + 63) / 64;
         const double R = nrows, Cn = bs + bs_next - (j0 + kDP);
         const double flops = Cn > 0 ? 2.0 * kDP * (Cn * R - Cn * (Cn - 1) / 2.0) * nc : 0.0;
         direct_flops_ += flops;
         const bool tev = timed && ev_i + 2 <= ev_upd_.size();
         if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
-        k_direct_update<<<dim3(T, T, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, j0, pglob, NP, d_dvec_);
+        if (Tc > 0) k_direct_update<<<dim3(Tc, nc), 128, kUpdateSmem, stream_>>>(d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, j0, pglob, NP, d_dvec_);
         if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
         ++launches_; ++direct_update_launches_;
       }
