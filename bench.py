@@ -86,6 +86,27 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def fp64_peak(dev):
+    """FP64 matrix peak measured in this run the way MEASURED_PEAKS.json measures bf16: cuBLAS GEMM
+    (torch.matmul, 6144^3, best of 5, CUDA events).  Nominal B200 figure is 37 TFLOP/s."""
+    import torch
+    try:
+        n = 6144
+        a = torch.randn((n, n), dtype=torch.float64, device=dev)
+        c = torch.randn((n, n), dtype=torch.float64, device=dev)
+        torch.matmul(a, c)
+        best = 1e30
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(a, c); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        del a, c
+        torch.cuda.empty_cache()
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12, "measured in this run: cuBLAS DGEMM 6144^3 (torch.matmul fp64), best of 5"
+    except Exception as exc:   # pragma: no cover
+        return 37.0, f"nominal B200 FP64 (measurement failed: {exc})"
+
+
 def hbm_peak():
     try:
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -150,6 +171,7 @@ def main():
     workload = (f"synthetic 3D Ned_RT, rough random field (seed {SEED}, sigma ln(10)/2), "
                 f"{n_total} coarse cells (global refinements {g_ref}) x {L} local refinements")
     config = {"workload": workload, "pairing": "NED_RT", "coarse_cells": n_total, "local_refinements": L,
+              "use_direct_solver_basis": args.solver == "direct",
               "partition": f"contiguous Morton chunks over {world} rank(s)",
               "cache": "inputs larger than L2 (per-step working set is GBs)"}
 
@@ -248,13 +270,32 @@ def main():
         e2e_value = n_total / (e_wall_ms / args.steps * 1e-3)
         st = stats[-1]
         n_fine_dofs = st["n_fine_dofs"]
-        # roofline of the dominant kernel (k_minres_spmm): algorithmic bytes per launch:
-        # every per-cell matrix value of the interior system once per iteration + rhs/solution amortised.
-        launches = max(1, st["krylov_spmm_launches"])
-        bytes_per_launch = st["krylov_matrix_bytes"] / launches
-        spmm_ms = st["krylov_ms_spmm"]
-        peak, peak_src = hbm_peak()
-        achieved = bytes_per_launch / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+        if args.solver == "minres":
+            # dominant kernel k_minres_spmm: algorithmic bytes per launch: every per-cell matrix
+            # value of the interior system once per iteration + rhs/solution amortised over the iterations.
+            launches = max(1, st["krylov_spmm_launches"])
+            bytes_per_launch = st["krylov_matrix_bytes"] / launches
+            spmm_ms = st["krylov_ms_spmm"]
+            peak, peak_src = hbm_peak()
+            achieved = bytes_per_launch / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": "k_minres_spmm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "bytes_per_launch": bytes_per_launch, "ms_per_launch": spmm_ms,
+                        "launches_per_step": int(launches)}
+        else:
+            # dominant kernel k_direct_update (FP64 tensor-core trailing update of the block LDL^T):
+            # algorithmic flops = 2 * 32 * (entries of the lower-triangular trailing region) per launch, summed
+            # over the launches that were bracketed by CUDA events (first sub-batch of the step).
+            peak, peak_src = fp64_peak(dev)
+            ms_upd = st["direct_ms_update"]
+            achieved = st["direct_flops_timed"] / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else 0.0
+            n_timed = max(1, st["direct_update_launches"] * st["direct_flops_timed"] / max(st["direct_flops"], 1.0))
+            roofline = {"bound": "tensor", "kernel": "k_direct_update", "achieved": achieved, "peak": peak,
+                        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                        "flops_per_step": st["direct_flops"], "flops_timed": st["direct_flops_timed"],
+                        "ms_timed": ms_upd, "launches_timed": int(round(n_timed)),
+                        "launches_per_step": int(st["direct_update_launches"]),
+                        "step_fp64_tflops": st["direct_flops"] / (ms_step * 1e-3) / 1e12}
         line = {
             "metric": "basis build throughput", "value": value, "unit": "coarse cells/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
@@ -267,10 +308,8 @@ def main():
                     "d2h_bytes_per_step": int(h_M.numel() * 8 + h_r.numel() * 8),
                     "timing": "host wall clock around msfec_build_basis (pinned host buffers in, host buffers out), max over ranks"},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
-            "roofline": {"bound": "hbm", "kernel": "k_minres_spmm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": spmm_ms,
-                         "launches_per_step": int(launches)},
+            "roofline": roofline,
+            "solver": args.solver,
             "phases_ms": {kk: st[kk] for kk in ("ms_assemble", "ms_lift", "ms_solve", "ms_gram")},
             "krylov": {"iterations_max": st["iterations_max"], "iterations_mean": st["iterations_mean"],
                        "residual_max": st["residual_max"], "not_converged": st["not_converged"]},
