@@ -148,60 +148,67 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kLDT = 72;   // shared-memory stride (doubles) of one panel column: 64 rows + 8 pad
-constexpr size_t kUpdateSmem = (3 * kDP * kLDT + kDP) * sizeof(double);
-
-// stage a 64-row x 32-column block of the panel (global: column-major, rows contiguous) into
-// shared memory [p][i]; rows >= ld are zero-filled.  128 threads, 8 x 16-byte chunks each.
-__device__ __forceinline__ void stage_block(double *dst, const double *P, int ld, int j0, int row0, int tid) {
+// stage a TROWS-row x 32-column block of one source panel (global: column-major, rows contiguous) into
+// shared memory [p][i] with row stride TROWS+8; rows >= ld are zero-filled.  128 threads.
+template <int TROWS>
+__device__ __forceinline__ void stage_block(double *dst, const double *P, int ld, int jsrc, int row0, int tid) {
+  constexpr int LDS = TROWS + 8, CPC = TROWS / 2;          // 16-byte chunks per column
 #pragma unroll
-  for (int t = 0; t < 8; ++t) {
-    const int chunk = tid + t * 128;        // 0..1023
-    const int p = chunk >> 5, i = (chunk & 31) * 2;
-    double *d = dst + p * kLDT + i;
-    if (row0 + i < ld) cp_async16(d, P + (size_t)(j0 + p) * ld + row0 + i);
+  for (int t = 0; t < CPC * kDP / 128; ++t) {
+    const int chunk = tid + t * 128;
+    const int p = chunk / CPC, i = (chunk % CPC) * 2;
+    double *d = dst + p * LDS + i;
+    if (row0 + i < ld) cp_async16(d, P + (size_t)(jsrc + p) * ld + row0 + i);
     else { d[0] = 0.0; d[1] = 0.0; }
   }
 }
 
-// C(vr, vc) -= sum_p L(vr, p) d_p L(vc, p) over the trailing region vr >= vc >= j0+32 of block
-// column s (virtual index space [slab s | slab s+1 | rhs rows]); targets in columns >= bs live in
-// block column s+1.  grid (Tc, cells): one CTA per 64-wide column strip; it keeps the (scaled on
-// the fly) column operand in shared memory and walks down the row tiles with a cp.async double
-// buffer; the C tile is loaded straight into the DMMA accumulators.  block 128 = 2x2 warps of
-// 32x32.
+template <int TM, int TN>
+constexpr size_t update_smem_bytes(int max_src) {
+  return ((size_t)max_src * kDP * (TN + 8) + 2 * (size_t)kDP * (TM + 8) + (size_t)max_src * kDP) * sizeof(double);
+}
+
+// C(vr, vc) -= sum_{p in source panels} L(vr, p) d_p L(vc, p) for target columns vc in [vc_lo, vc_hi) and
+// rows vr >= vc of block column s (virtual index space [slab s | slab s+1 | rhs rows]); targets in
+// columns >= bs live in block column s+1.  The nq source panels (32 columns each, starting at jsrc) are
+// applied in one pass so every C tile is read and written once per window (K = 32 nq).
+// grid (column tiles, row splits Z, cells); block 128 = (TM/32) x (TN/32) warps of 32x32.  A CTA keeps
+// the column operands of all source panels in shared memory and walks its row tiles with a cp.async
+// double buffer; the C tile is loaded straight into the DMMA accumulators.
+template <int TM, int TN>
 __global__ void __launch_bounds__(128)
 k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int bs, int bs_next,
-                long long col_off_next, int ld_next, int rhs_row_next, int j0, int pglob, int NP,
-                const double *__restrict__ dvec) {
+                long long col_off_next, int ld_next, int rhs_row_next, int jsrc, int nq, int vc_lo, int vc_hi,
+                int pglob, int NP, const double *__restrict__ dvec) {
+  constexpr int LDR = TM + 8, LDC = TN + 8, WN = TN / 32;
   extern __shared__ __align__(16) double upd_smem[];
-  double *Lc = upd_smem;
-  double (*Lr)[kDP * kLDT] = reinterpret_cast<double (*)[kDP * kLDT]>(upd_smem + kDP * kLDT);
-  double *dsm = upd_smem + 3 * kDP * kLDT;
-  const int tj = blockIdx.x, cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int v0 = j0 + kDP;
-  const int cbase = v0 + tj * 64;
-  const int T = (ld - v0 + 63) / 64;
+  double *Lc = upd_smem;                                   // [nq][32][LDC]
+  double *Lr = Lc + (size_t)nq * kDP * LDC;                // [2][32][LDR]
+  double *dsm = Lr + 2 * kDP * LDR;                        // [nq*32]
+  const int tj = blockIdx.x, cell = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cbase = vc_lo + tj * TN;
   double *cb = band + (size_t)cell * band_stride;
   const double *P = cb + col_off;
-  if (tid < kDP) dsm[tid] = dvec[(size_t)cell * NP + pglob + tid];
-  stage_block(Lc, P, ld, j0, cbase, tid);
-  stage_block(Lr[0], P, ld, j0, cbase, tid);
+  // row tiles of this CTA: rbase = r_first + (z + Z*i) * TM, first tile contains row cbase
+  const int r_first = cbase - (cbase - vc_lo) % TM;        // TM-aligned relative to vc_lo
+  const int T = (ld - r_first + TM - 1) / TM;
+  const int Z = gridDim.y;
+  if ((int)blockIdx.y >= T) return;
+  for (int i = tid; i < nq * kDP; i += 128) dsm[i] = dvec[(size_t)cell * NP + pglob + i];
+  for (int q = 0; q < nq; ++q) stage_block<TN>(Lc + (size_t)q * kDP * LDC, P, ld, jsrc + q * kDP, cbase, tid);
+  stage_block<TM>(Lr, P, ld, jsrc, r_first + blockIdx.y * TM, tid);
   cp_async_commit();
-  const int wr = warp >> 1, wc = warp & 1;
+  const int wr = warp / WN, wc = warp % WN;
   const int fr = lane >> 2, fk = lane & 3;
   const int vc0 = cbase + wc * 32;
-  const bool col_ok = vc0 < bs + bs_next;
-  // destination columns of this warp (uniform): block column s or s+1
+  const bool col_ok = vc0 < vc_hi && vc0 < bs + bs_next;
   double *cdst;
   int ldc;
   if (vc0 < bs) { cdst = cb + col_off + (size_t)vc0 * ld; ldc = ld; }
   else { cdst = cb + col_off_next + (size_t)(vc0 - bs) * ld_next; ldc = ld_next; }
-  for (int ti = tj; ti < T; ++ti) {
-    const int buf = (ti - tj) & 1;
-    const int rbase = v0 + ti * 64;
-    if (ti + 1 < T) stage_block(Lr[buf ^ 1], P, ld, j0, rbase + 64, tid);
-    cp_async_commit();
+  int buf = 0;
+  for (int ti = blockIdx.y; ti < T; ti += Z) {
+    const int rbase = r_first + ti * TM;
     const int vr0 = rbase + wr * 32;
     const bool active = col_ok && vr0 >= vc0 && vr0 < ld;
     int roff = vr0;
@@ -216,26 +223,37 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
           for (int h = 0; h < 2; ++h)
             acc[mt][nt][h] = cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr];
     }
-    cp_async_wait<1>();
-    __syncthreads();
-    if (active) {
-      const double *A = Lr[buf] + wr * 32 + fr;
-      const double *B = Lc + wc * 32 + fr;
+    for (int q = 0; q < nq; ++q) {
+      // prefetch the next (row tile, source panel) operand block
+      if (q + 1 < nq) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, jsrc + (q + 1) * kDP, rbase, tid);
+      else if (ti + Z < T) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, jsrc, rbase + Z * TM, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      if (active) {
+        const double *A = Lr + buf * kDP * LDR + wr * 32 + fr;
+        const double *B = Lc + (size_t)q * kDP * LDC + wc * 32 + fr;
+        const double *dq = dsm + q * kDP;
 #pragma unroll
-      for (int ks = 0; ks < kDP / 4; ++ks) {
-        const int kk = ks * 4 + fk;
-        const double dk = dsm[kk];
-        double af[4], bf[4];
+        for (int ks = 0; ks < kDP / 4; ++ks) {
+          const int kk = ks * 4 + fk;
+          const double dk = dq[kk];
+          double af[4], bf[4];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          af[t] = -A[kk * kLDT + t * 8];
-          bf[t] = B[kk * kLDT + t * 8] * dk;
+          for (int t = 0; t < 4; ++t) {
+            af[t] = -A[kk * LDR + t * 8];
+            bf[t] = B[kk * LDC + t * 8] * dk;
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
         }
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
+      __syncthreads();
+      buf ^= 1;
+    }
+    if (active) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -244,7 +262,6 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
           for (int h = 0; h < 2; ++h)
             cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr] = acc[mt][nt][h];
     }
-    __syncthreads();
   }
   cp_async_wait<0>();
 }

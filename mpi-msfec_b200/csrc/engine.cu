@@ -590,7 +590,9 @@ class Engine {
       d_dp_inv_ = dev_upload(P_.inv_perm); d_dp_cdest_ = dev_upload(P_.cell_dest); d_dp_cref_ = dev_upload(P_.cell_ref);
       d_dp_sdest_ = dev_upload(P_.shared_dest); d_dp_sval_ = dev_upload(P_.shared_val);
       d_dp_kdest_ = dev_upload(P_.const_dest); d_dp_kval_ = dev_upload(P_.const_val); d_dp_rhs_ = dev_upload(P_.rhs_dest);
-      CUDA_OK(cudaFuncSetAttribute(k_direct_update, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpdateSmem));
+      if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(4, std::atoi(w)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(4)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(4)));
       ev_upd_.resize(2048);
       for (auto &ev : ev_upd_) CUDA_OK(cudaEventCreate(&ev));
     }
@@ -661,6 +663,7 @@ class Engine {
   // direct solver
   bool use_direct_ = false;
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
+  int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
   int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr;
   long long *d_dp_col_ = nullptr;
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
@@ -834,27 +837,50 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     launches_ += 4;
     size_t ev_i = 0;
     std::vector<double> ev_flops;
-    for (int s = 0; s < P_.n_slabs; ++s) {
+    auto launch_update = [&](int s, int jsrc, int nq, int vc_lo, int vc_hi, bool strip) {
       const int bs = P_.bs[s], ld = P_.ld[s];
       const int bs_next = s + 1 < P_.n_slabs ? P_.bs[s + 1] : 0;
       const long long co_next = s + 1 < P_.n_slabs ? P_.col_off[s + 1] : 0;
       const int ld_next = s + 1 < P_.n_slabs ? P_.ld[s + 1] : 0;
       const int rhs_row_next = ld_next - DirectPlan::kRhsRows;
-      for (int j0 = 0; j0 < bs; j0 += kDP) {
-        const int pglob = P_.slab_off[s] + j0;
-        const int nrows = ld - (j0 + kDP);
-        k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_flag_ + 2);
-        k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_);
-        launches_ += 2;
-        const int Tc = (bs + bs_next - (j0 + kDP) + 63) / 64;
-        const double R = nrows, Cn = bs + bs_next - (j0 + kDP);
-        const double flops = Cn > 0 ? 2.0 * kDP * (Cn * R - Cn * (Cn - 1) / 2.0) * nc : 0.0;
-        direct_flops_ += flops;
-        const bool tev = timed && ev_i + 2 <= ev_upd_.size();
-        if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
-        if (Tc > 0) k_direct_update<<<dim3(Tc, nc), 128, kUpdateSmem, stream_>>>(d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, j0, pglob, NP, d_dvec_);
-        if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
-        ++launches_; ++direct_update_launches_;
+      const int c_hi = std::min(vc_hi, bs + bs_next);
+      if (c_hi <= vc_lo) return;
+      // algorithmic flops: 2 * K * (entries vr >= vc of the target region)
+      const double R = ld - vc_lo, Cn = c_hi - vc_lo;
+      const double flops = 2.0 * kDP * nq * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
+      direct_flops_ += flops;
+      const bool tev = timed && ev_i + 2 <= ev_upd_.size();
+      if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
+      const int pglob = P_.slab_off[s] + jsrc;
+      if (strip) {
+        const int T = (ld - vc_lo + 127) / 128;
+        k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
+            d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, jsrc, nq, vc_lo, c_hi, pglob, NP, d_dvec_);
+      } else {
+        const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 63) / 64;
+        int Z = std::max(1, std::min(T, (4 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));   // aim at >= ~16 CTAs per SM
+        k_direct_update<64, 64><<<dim3(Tc, Z, nc), 128, update_smem_bytes<64, 64>(nq), stream_>>>(
+            d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, jsrc, nq, vc_lo, c_hi, pglob, NP, d_dvec_);
+      }
+      if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
+      ++launches_; ++direct_update_launches_;
+    };
+    for (int s = 0; s < P_.n_slabs; ++s) {
+      const int bs = P_.bs[s], ld = P_.ld[s];
+      const int n_panels = bs / kDP;
+      for (int p0 = 0; p0 < n_panels; p0 += direct_window_) {
+        const int pe = std::min(n_panels, p0 + direct_window_);
+        for (int j = p0; j < pe; ++j) {
+          const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
+          // bring panel j up to date with the earlier panels of this window, then factor it
+          if (j > p0) launch_update(s, p0 * kDP, j - p0, j0, j0 + kDP, true);
+          const int nrows = ld - (j0 + kDP);
+          k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_flag_ + 2);
+          k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_);
+          launches_ += 2;
+        }
+        // apply the whole window to everything behind it (rest of slab s, slab s+1, rhs rows)
+        launch_update(s, p0 * kDP, pe - p0, pe * kDP, 1 << 30, false);
       }
     }
     k_direct_backward<<<nc, 256, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);

@@ -156,7 +156,7 @@ def test_cpp_host_driver(msfec, tmp_path):
         subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
     txt = open(prm_path("NED_RT")).read().replace("set local refinements = 4", "set local refinements = 2")
     txt = txt.replace("set use direct solver basis = false", "set use direct solver basis = true")
-    txt = txt.replace("set dirname output = data_test-01_NED-RT\nend\n\nsubsection Equation", f"set dirname output = {tmp_path}/out\nend\n\nsubsection Equation")
+    txt = txt.replace("set dirname output = data_test-01_NED-RT", f"set dirname output = {tmp_path}/out")
     prm = tmp_path / "t.prm"
     prm.write_text(txt)
     got = {}
@@ -177,3 +177,34 @@ def test_cpp_host_driver(msfec, tmp_path):
     # error path of the CLI
     r = subprocess.run([exe, "-x"], capture_output=True, text=True)
     assert r.returncode == 1
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_reference_prm_configs_full_size(msfec, pairing):
+    """BASELINE configs[0..3] at their real size: the reference's prm_*_test-01.prm (64 coarse cells,
+    4 local refinements, n = 16) through the direct path; two cells against the oracle, structure on all."""
+    cells = mo.morton_cells(2)
+    p = msfec.problem_from_prm(os.path.join(ROOT, "examples", "prm", {"Q": "prm_q_test-01.prm", "Q_NED": "prm_q_ned_test-01.prm",
+                               "NED_RT": "prm_ned_rt_test-01.prm", "RT_DQ": "prm_rt_dq_test-01.prm"}[pairing]), pairing)
+    assert p.n_refine_local == 4
+    p.use_direct_solver_basis = 1
+    bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(64))
+    M = bb.get_global_element_matrix()
+    assert np.isfinite(M).all()
+    k0 = {"Q": 8, "Q_NED": 8, "NED_RT": 12, "RT_DQ": 6}[pairing]
+    s = np.abs(M).max(axis=(1, 2))
+    assert (np.abs(M[:, :k0, :k0] - M[:, :k0, :k0].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    worst = _check_cells(bb, oracle_problem(pairing, 4), cells, np.arange(64), (37,) if pairing == "NED_RT" else (5, 37))
+    print(pairing, "L=4 worst", worst, bb.stats)
+    assert worst < TOL
+
+
+@pytest.mark.parametrize("pairing", ["Q", "RT_DQ"])
+def test_minres_full_size(msfec, pairing):
+    """The iterative path ('use direct solver basis = false', as shipped in the reference .prm) at n = 16."""
+    cells = mo.morton_cells(2)[:32]
+    p = lib_problem(msfec, pairing, 4)
+    bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(32))
+    worst = _check_cells(bb, oracle_problem(pairing, 4), cells, np.arange(32), (5,))
+    print(pairing, "L=4 minres worst", worst, bb.stats["iterations_max"])
+    assert worst < TOL and bb.stats["solver"] == 0
