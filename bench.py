@@ -120,6 +120,12 @@ def hbm_peak():
 # ------------------------------------------------------------------------------------------
 def _oracle_worker(args):
     lo, hi, g_ref, L = args
+    # one BLAS/OpenMP thread per worker process: the pool already uses every core
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     from oracle import msfec_oracle as mo
     prob = mo.Problem(pairing="NED_RT", n_refine_local=L, n_refine_global=g_ref, random_field_seed=SEED,
                       rhs_expr=RHS, rhs_constants={"scale": 100.0})
@@ -136,7 +142,10 @@ def cpu_oracle_throughput(n_sample, g_ref, L, cores):
     import multiprocessing as mp
     per = max(1, n_sample // cores)
     jobs = [(i * per, (i + 1) * per, g_ref, L) for i in range(cores)]
-    with mp.get_context("fork").Pool(cores) as pool:
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    # spawn: never fork a process that has initialised CUDA
+    with mp.get_context("spawn").Pool(cores) as pool:
         pool.map(_oracle_worker, [(0, 1, g_ref, L)] * cores)     # warm imports / topology caches
         t0 = time.perf_counter()
         pool.map(_oracle_worker, jobs)
@@ -179,7 +188,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        n_sample = args.cpu_sample or 8 * cores
+        n_sample = args.cpu_sample or 64 * cores
         vals = []
         for _ in range(args.warmup + args.steps):
             v, n_done, dt = cpu_oracle_throughput(n_sample, g_ref, L, cores)
@@ -315,7 +324,7 @@ def main():
                        "residual_max": st["residual_max"], "not_converged": st["not_converged"]},
         }
         if not args.no_cpu_baseline and world == 1:
-            n_sample = args.cpu_sample or 8 * cores
+            n_sample = args.cpu_sample or 64 * cores
             v, n_done, dt = cpu_oracle_throughput(n_sample, g_ref, L, cores)
             line["cpu_baseline"] = {"value": v, "unit": "coarse cells/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_done} cells of the same workload in {dt:.1f} s, "
