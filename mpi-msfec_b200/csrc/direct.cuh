@@ -213,7 +213,13 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
     const bool active = col_ok && vr0 >= vc0 && vr0 < ld;
     int roff = vr0;
     if (vc0 >= bs) roff = vr0 < bs + bs_next ? vr0 - bs : rhs_row_next + (vr0 - bs - bs_next);
-    double acc[4][4][2];
+    // C is fetched into its own registers now and consumed after the MMAs, so its latency hides
+    // behind the nq source panels; the product is accumulated from zero with a negated A operand.
+    double acc[4][4][2], cold[4][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
     if (active) {
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
@@ -221,7 +227,7 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            acc[mt][nt][h] = cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr];
+            cold[mt][nt][h] = cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr];
     }
     for (int q = 0; q < nq; ++q) {
       // prefetch the next (row tile, source panel) operand block
@@ -260,7 +266,7 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
         for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
           for (int h = 0; h < 2; ++h)
-            cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr] = acc[mt][nt][h];
+            cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr] = cold[mt][nt][h] + acc[mt][nt][h];
     }
   }
   cp_async_wait<0>();
@@ -273,19 +279,19 @@ struct DirectPlanDev {
   const long long *col_off;
 };
 
-// L^T x = z.  One CTA (256 threads) per cell; xT[cell][j][NP] is both output and the running
-// solution read by later (lower-numbered) panels.  Per panel: (1) t = z - L(below)^T x with the
-// L rows staged through shared memory (lane = panel column, warp w owns rhs w, w+8, w+16), (2)
-// unit upper-triangular solve with the diagonal block, one thread per rhs, column oriented.
-__global__ void __launch_bounds__(256, 3)
+// L^T x = z.  One CTA (128 threads) per cell; xT[cell][j][NP] is both output and the running
+// solution read by later (lower-numbered) panels.  Per panel of 32 columns:
+//  (1) T = Z - L(below)^T X as a (32 x K) x (K x 24) product on the FP64 tensor cores; the K rows
+//      below the panel are split over the 4 warps, DMMA fragments are read straight from global
+//      memory (each quad of lanes reads one full 32-byte sector), partial sums meet in shared memory;
+//  (2) unit upper-triangular solve with the 32x32 diagonal block, one thread per rhs, column oriented.
+__global__ void __launch_bounds__(128, 6)
 k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, const double *__restrict__ diagL,
                   int k, double *xT) {
-  constexpr int CH = 64;
-  __shared__ double Ls[CH][kDP + 1];
-  __shared__ double xs[CH][kMaxK + 1];
-  __shared__ double tt[kDP][kMaxK + 1];
+  __shared__ double tt[kDP][24 + 1];
   __shared__ double Ld[kDP][kDP + 1];
   const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
   const int NP = D.NP;
   double *x = xT + (size_t)cell * k * NP;
   for (int s = D.n_slabs - 1; s >= 0; --s) {
@@ -293,36 +299,52 @@ k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPla
     const int rows_dof = ld - DirectPlan::kRhsRows, rhs_row = rows_dof;
     const double *P = band + (size_t)cell * band_stride + D.col_off[s];
     for (int j0 = bs - kDP; j0 >= 0; j0 -= kDP) {
-      double acc[3] = {0.0, 0.0, 0.0};
-      for (int r0 = j0 + kDP; r0 < rows_dof; r0 += CH) {
-        {   // stage CH rows x 32 columns of L and CH rows x k of x
-          const int i = tid & (CH - 1), cg = tid >> 6;
-          const bool ok = r0 + i < rows_dof;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) Ls[i][cg * 8 + q] = ok ? P[(size_t)(j0 + cg * 8 + q) * ld + r0 + i] : 0.0;
-          for (int j = cg; j < k; j += 4) xs[i][j] = ok ? x[(size_t)j * NP + so + r0 + i] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int i = 0; i < CH; ++i) {
-          const double l = Ls[i][lane];
-#pragma unroll
-          for (int jj = 0; jj < 3; ++jj) {
-            const int j = warp + 8 * jj;
-            if (j < k) acc[jj] = fma(l, xs[i][j], acc[jj]);
-          }
-        }
-        __syncthreads();
-      }
-#pragma unroll
-      for (int jj = 0; jj < 3; ++jj) {
-        const int j = warp + 8 * jj;
-        if (j < k) tt[lane][j] = P[(size_t)(j0 + lane) * ld + rhs_row + j] - acc[jj];
+      // tt := z (rhs rows of the panel columns), padded rhs columns := 0
+      for (int idx = tid; idx < kDP * 24; idx += 128) {
+        const int c = idx / 24, j = idx % 24;
+        tt[c][j] = j < k ? P[(size_t)(j0 + c) * ld + rhs_row + j] : 0.0;
       }
       const double *dl = diagL + ((size_t)cell * NP + so + j0) * kDP;
-      for (int idx = tid; idx < kDP * kDP; idx += 256) {
+      for (int idx = tid; idx < kDP * kDP; idx += 128) {
         const int i = idx & 31, p = idx >> 5;
         Ld[i][p] = dl[(size_t)p * kDP + i];
+      }
+      __syncthreads();
+      const int r_lo = j0 + kDP, nsteps = (rows_dof - r_lo) / 4;       // rows_dof, r_lo multiples of 32
+      if (nsteps > 0) {
+        double acc[4][3][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        // rows are multiples of 32, so nsteps is a multiple of 8: each of the 4 warps takes pairs of k-steps
+        // and keeps two of them (14 independent sector loads) in flight
+        for (int st = warp * 2; st < nsteps; st += 8) {
+          double af[2][4], bf[2][3];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int i = r_lo + (st + u) * 4 + fk;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[u][mt] = P[(size_t)(j0 + mt * 8 + fr) * ld + i];   // A[m=c][k=i] = L(i, c)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+              const int j = nt * 8 + fr;
+              bf[u][nt] = j < k ? x[(size_t)j * NP + so + i] : 0.0;                              // B[k=i][n=j] = x_i^(j)
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+              for (int nt = 0; nt < 3; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[u][mt], bf[u][nt]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) atomicAdd(&tt[mt * 8 + fr][nt * 8 + fk * 2 + h], -acc[mt][nt][h]);
       }
       __syncthreads();
       if (tid < k) {

@@ -825,8 +825,11 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
   CUDA_OK(cudaMemsetAsync(d_vec_[7], 0, (size_t)groups * NI * k * kLanes * sizeof(double), stream_));
   DirectPlanDev D{P_.n_slabs, NP, d_dp_bs_, d_dp_off_, d_dp_ld_, d_dp_col_};
   bool timed = (direct_update_launches_ == 0);   // per-launch events on the first sub-batch of a build
-  for (int lo = 0; lo < nb; lo += direct_sub_) {
-    const int hi = std::min(nb, lo + direct_sub_), nc = hi - lo;
+  // equal-sized sub-batches (multiples of 32 cells) so that no ragged tail runs at low occupancy
+  const int n_sub = (nb + direct_sub_ - 1) / direct_sub_;
+  const int sub = std::min(direct_sub_, ((nb + n_sub - 1) / n_sub + kLanes - 1) / kLanes * kLanes);
+  for (int lo = 0; lo < nb; lo += sub) {
+    const int hi = std::min(nb, lo + sub), nc = hi - lo;
     const int g0 = lo / kLanes, ng = (hi + kLanes - 1) / kLanes - g0;
     CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
     const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
@@ -883,7 +886,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
         launch_update(s, p0 * kDP, pe - p0, pe * kDP, 1 << 30, false);
       }
     }
-    k_direct_backward<<<nc, 256, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);
+    k_direct_backward<<<nc, 128, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);
     k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
     launches_ += 2;
     if (timed) {
