@@ -204,7 +204,12 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
     ctx = new msfec_ctx();
     ctx->topo = build_topology(p->pairing, 1 << p->n_refine_local);
     make_spec(*p, ctx->topo, ctx->spec);
-    ctx->plan = build_direct_plan(ctx->topo);
+    {
+      // RT_DQ: a layer block alone is a pure-Neumann sub-problem (singular pivot); keep layer + plane together
+      int ordering = p->pairing == MSFEC_RT_DQ ? 1 : 0;
+      if (const char *e = std::getenv("MSFEC_DIRECT_ORDERING")) ordering = std::string(e) == "slab" ? 1 : ordering;
+      ctx->plan = build_direct_plan(ctx->topo, ordering);
+    }
     if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan);
     *out = ctx;
     return MSFEC_OK;
@@ -313,6 +318,9 @@ int msfec_debug_table(const msfec_ctx *ctx, const char *name, void *out, size_t 
   else if (n == "direct.cell_ref") iv = &dp.cell_ref; else if (n == "direct.shared_dest") iv = &dp.shared_dest;
   else if (n == "direct.shared_val") dv = &dp.shared_val; else if (n == "direct.const_dest") iv = &dp.const_dest;
   else if (n == "direct.const_val") dv = &dp.const_val; else if (n == "direct.rhs_dest") iv = &dp.rhs_dest;
+  else if (n == "direct.front_rows") iv = &dp.front_rows; else if (n == "direct.chunk_off") iv = &dp.chunk_off;
+  else if (n == "direct.chunk_blk") iv = &dp.chunk_blk; else if (n == "direct.chunk_local") iv = &dp.chunk_local;
+  else if (n == "direct.front_pos") iv = &dp.front_pos;
   else if (n == "direct.col_off") { for (auto v : dp.col_off) col_off32.push_back((int32_t)v); iv = &col_off32; }
   if (n == "G") dv = &t.G; else if (n == "F1") dv = &t.F1;
   else if (n == "diag_slot0") iv = &t.diag_slot0; else if (n == "diag_slot1") iv = &t.diag_slot1;

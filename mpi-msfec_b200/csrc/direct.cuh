@@ -163,6 +163,14 @@ __device__ __forceinline__ void stage_block(double *dst, const double *P, int ld
   }
 }
 
+// Device copy of the block structure (DirectPlan): all lookups below are warp-uniform.
+struct DirectPlanDev {
+  int n_slabs, NP;
+  const int *bs, *slab_off, *ld, *front_rows;
+  const long long *col_off;
+  const int *chunk_off, *chunk_blk, *chunk_local, *front_pos;
+};
+
 template <int TM, int TN>
 constexpr size_t update_smem_bytes(int max_src) {
   return ((size_t)max_src * kDP * (TN + 8) + 2 * (size_t)kDP * (TM + 8) + (size_t)max_src * kDP) * sizeof(double);
@@ -177,9 +185,8 @@ constexpr size_t update_smem_bytes(int max_src) {
 // double buffer; the C tile is loaded straight into the DMMA accumulators.
 template <int TM, int TN>
 __global__ void __launch_bounds__(128)
-k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int bs, int bs_next,
-                long long col_off_next, int ld_next, int rhs_row_next, int jsrc, int nq, int vc_lo, int vc_hi,
-                int pglob, int NP, const double *__restrict__ dvec) {
+k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int vc_lo,
+                int vc_hi, const double *__restrict__ dvec) {
   constexpr int LDR = TM + 8, LDC = TN + 8, WN = TN / 32;
   extern __shared__ __align__(16) double upd_smem[];
   double *Lc = upd_smem;                                   // [nq][32][LDC]
@@ -187,6 +194,9 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
   double *dsm = Lr + 2 * kDP * LDR;                        // [nq*32]
   const int tj = blockIdx.x, cell = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cbase = vc_lo + tj * TN;
+  const int ld = D.ld[s], front_rows = D.front_rows[s], NP = D.NP, pglob = D.slab_off[s] + jsrc;
+  const long long col_off = D.col_off[s];
+  const int choff = D.chunk_off[s];
   double *cb = band + (size_t)cell * band_stride;
   const double *P = cb + col_off;
   // row tiles of this CTA: rbase = r_first + (z + Z*i) * TM, first tile contains row cbase
@@ -201,18 +211,26 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
   const int wr = warp / WN, wc = warp % WN;
   const int fr = lane >> 2, fk = lane & 3;
   const int vc0 = cbase + wc * 32;
-  const bool col_ok = vc0 < vc_hi && vc0 < bs + bs_next;
-  double *cdst;
-  int ldc;
-  if (vc0 < bs) { cdst = cb + col_off + (size_t)vc0 * ld; ldc = ld; }
-  else { cdst = cb + col_off_next + (size_t)(vc0 - bs) * ld_next; ldc = ld_next; }
+  const bool col_ok = vc0 < vc_hi && vc0 < front_rows;
+  // destination of this warp's columns: block column s itself, or the block column of the reached block
+  double *cdst = cb;
+  int ldc = ld, cblk = s;
+  if (col_ok) {
+    cblk = D.chunk_blk[choff + (vc0 >> 5)];
+    if (cblk == s) cdst = cb + col_off + (size_t)vc0 * ld;
+    else { ldc = D.ld[cblk]; cdst = cb + D.col_off[cblk] + (size_t)D.chunk_local[choff + (vc0 >> 5)] * ldc; }
+  }
   int buf = 0;
   for (int ti = blockIdx.y; ti < T; ti += Z) {
     const int rbase = r_first + ti * TM;
     const int vr0 = rbase + wr * 32;
     const bool active = col_ok && vr0 >= vc0 && vr0 < ld;
     int roff = vr0;
-    if (vc0 >= bs) roff = vr0 < bs + bs_next ? vr0 - bs : rhs_row_next + (vr0 - bs - bs_next);
+    if (active && cblk != s) {
+      const int rb = D.chunk_blk[choff + (vr0 >> 5)];
+      roff = rb < 0 ? D.front_rows[cblk] + (vr0 - front_rows)
+                    : D.front_pos[cblk * D.n_slabs + rb] + D.chunk_local[choff + (vr0 >> 5)];
+    }
     // C is fetched into its own registers now and consumed after the MMAs, so its latency hides
     // behind the nq source panels; the product is accumulated from zero with a negated A operand.
     double acc[4][4][2], cold[4][4][2];
@@ -273,12 +291,6 @@ k_direct_update(double *__restrict__ band, size_t band_stride, long long col_off
 }
 
 // ---- backward substitution -------------------------------------------------------------
-struct DirectPlanDev {
-  int n_slabs, NP;
-  const int *bs, *slab_off, *ld;
-  const long long *col_off;
-};
-
 // L^T x = z.  One CTA (128 threads) per cell; xT[cell][j][NP] is both output and the running
 // solution read by later (lower-numbered) panels.  Per panel of 32 columns:
 //  (1) T = Z - L(below)^T X as a (32 x K) x (K x 24) product on the FP64 tensor cores; the K rows
@@ -295,8 +307,8 @@ k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPla
   const int NP = D.NP;
   double *x = xT + (size_t)cell * k * NP;
   for (int s = D.n_slabs - 1; s >= 0; --s) {
-    const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s];
-    const int rows_dof = ld - DirectPlan::kRhsRows, rhs_row = rows_dof;
+    const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s], choff = D.chunk_off[s];
+    const int rows_dof = D.front_rows[s], rhs_row = rows_dof;
     const double *P = band + (size_t)cell * band_stride + D.col_off[s];
     for (int j0 = bs - kDP; j0 >= 0; j0 -= kDP) {
       // tt := z (rhs rows of the panel columns), padded rhs columns := 0
@@ -324,12 +336,14 @@ k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPla
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             const int i = r_lo + (st + u) * 4 + fk;
+            const int ch = choff + (i >> 5);                  // front row -> padded unknown index
+            const int xi = D.slab_off[D.chunk_blk[ch]] + D.chunk_local[ch] + (i & 31);
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) af[u][mt] = P[(size_t)(j0 + mt * 8 + fr) * ld + i];   // A[m=c][k=i] = L(i, c)
 #pragma unroll
             for (int nt = 0; nt < 3; ++nt) {
               const int j = nt * 8 + fr;
-              bf[u][nt] = j < k ? x[(size_t)j * NP + so + i] : 0.0;                              // B[k=i][n=j] = x_i^(j)
+              bf[u][nt] = j < k ? x[(size_t)j * NP + xi] : 0.0;                                  // B[k=i][n=j] = x_i^(j)
             }
           }
 #pragma unroll

@@ -585,6 +585,8 @@ class Engine {
     if (const char *e = std::getenv("MSFEC_FORCE_SOLVER")) use_direct_ = std::string(e) == "direct";
     if (use_direct_) {
       d_dp_bs_ = dev_upload(P_.bs); d_dp_off_ = dev_upload(P_.slab_off); d_dp_ld_ = dev_upload(P_.ld);
+      d_dp_front_ = dev_upload(P_.front_rows); d_dp_choff_ = dev_upload(P_.chunk_off); d_dp_chblk_ = dev_upload(P_.chunk_blk);
+      d_dp_chloc_ = dev_upload(P_.chunk_local); d_dp_fpos_ = dev_upload(P_.front_pos);
       std::vector<long long> co(P_.col_off.begin(), P_.col_off.end());
       d_dp_col_ = dev_upload(co);
       d_dp_inv_ = dev_upload(P_.inv_perm); d_dp_cdest_ = dev_upload(P_.cell_dest); d_dp_cref_ = dev_upload(P_.cell_ref);
@@ -604,6 +606,7 @@ class Engine {
     cudaSetDevice(device_);
     free_batch(); free_store(); free_direct();
     for (auto &ev : ev_upd_) cudaEventDestroy(ev);
+    cudaFree(d_dp_front_); cudaFree(d_dp_choff_); cudaFree(d_dp_chblk_); cudaFree(d_dp_chloc_); cudaFree(d_dp_fpos_);
     cudaFree(d_dp_bs_); cudaFree(d_dp_off_); cudaFree(d_dp_ld_); cudaFree(d_dp_col_); cudaFree(d_dp_inv_);
     cudaFree(d_dp_cdest_); cudaFree(d_dp_cref_); cudaFree(d_dp_sdest_); cudaFree(d_dp_sval_); cudaFree(d_dp_kdest_);
     cudaFree(d_dp_kval_); cudaFree(d_dp_rhs_);
@@ -664,7 +667,8 @@ class Engine {
   bool use_direct_ = false;
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
   int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
-  int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr;
+  int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr, *d_dp_front_ = nullptr, *d_dp_choff_ = nullptr,
+      *d_dp_chblk_ = nullptr, *d_dp_chloc_ = nullptr, *d_dp_fpos_ = nullptr;
   long long *d_dp_col_ = nullptr;
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
       *d_dp_rhs_ = nullptr;
@@ -823,7 +827,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
   const int k = T_.k_solve, NI = T_.NI, NP = P_.NP;
   const size_t stride = (size_t)P_.band_doubles;
   CUDA_OK(cudaMemsetAsync(d_vec_[7], 0, (size_t)groups * NI * k * kLanes * sizeof(double), stream_));
-  DirectPlanDev D{P_.n_slabs, NP, d_dp_bs_, d_dp_off_, d_dp_ld_, d_dp_col_};
+  DirectPlanDev D{P_.n_slabs, NP, d_dp_bs_, d_dp_off_, d_dp_ld_, d_dp_front_, d_dp_col_, d_dp_choff_, d_dp_chblk_, d_dp_chloc_, d_dp_fpos_};
   bool timed = (direct_update_launches_ == 0);   // per-launch events on the first sub-batch of a build
   // equal-sized sub-batches (multiples of 32 cells) so that no ragged tail runs at low occupancy
   const int n_sub = (nb + direct_sub_ - 1) / direct_sub_;
@@ -841,12 +845,8 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     size_t ev_i = 0;
     std::vector<double> ev_flops;
     auto launch_update = [&](int s, int jsrc, int nq, int vc_lo, int vc_hi, bool strip) {
-      const int bs = P_.bs[s], ld = P_.ld[s];
-      const int bs_next = s + 1 < P_.n_slabs ? P_.bs[s + 1] : 0;
-      const long long co_next = s + 1 < P_.n_slabs ? P_.col_off[s + 1] : 0;
-      const int ld_next = s + 1 < P_.n_slabs ? P_.ld[s + 1] : 0;
-      const int rhs_row_next = ld_next - DirectPlan::kRhsRows;
-      const int c_hi = std::min(vc_hi, bs + bs_next);
+      const int ld = P_.ld[s];
+      const int c_hi = std::min(vc_hi, P_.front_rows[s]);
       if (c_hi <= vc_lo) return;
       // algorithmic flops: 2 * K * (entries vr >= vc of the target region)
       const double R = ld - vc_lo, Cn = c_hi - vc_lo;
@@ -854,16 +854,15 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       direct_flops_ += flops;
       const bool tev = timed && ev_i + 2 <= ev_upd_.size();
       if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
-      const int pglob = P_.slab_off[s] + jsrc;
       if (strip) {
         const int T = (ld - vc_lo + 127) / 128;
         k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
-            d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, jsrc, nq, vc_lo, c_hi, pglob, NP, d_dvec_);
+            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_dvec_);
       } else {
         const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 63) / 64;
         int Z = std::max(1, std::min(T, (4 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));   // aim at >= ~16 CTAs per SM
         k_direct_update<64, 64><<<dim3(Tc, Z, nc), 128, update_smem_bytes<64, 64>(nq), stream_>>>(
-            d_band_, stride, P_.col_off[s], ld, bs, bs_next, co_next, ld_next, rhs_row_next, jsrc, nq, vc_lo, c_hi, pglob, NP, d_dvec_);
+            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_dvec_);
       }
       if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
       ++launches_; ++direct_update_launches_;
@@ -871,8 +870,11 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     for (int s = 0; s < P_.n_slabs; ++s) {
       const int bs = P_.bs[s], ld = P_.ld[s];
       const int n_panels = bs / kDP;
-      for (int p0 = 0; p0 < n_panels; p0 += direct_window_) {
-        const int pe = std::min(n_panels, p0 + direct_window_);
+      // equal windows of at most direct_window_ panels (5 panels -> 3 + 2, 6 -> 3 + 3)
+      const int n_win = (n_panels + direct_window_ - 1) / direct_window_;
+      const int win = (n_panels + n_win - 1) / n_win;
+      for (int p0 = 0; p0 < n_panels; p0 += win) {
+        const int pe = std::min(n_panels, p0 + win);
         for (int j = p0; j < pe; ++j) {
           const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
           // bring panel j up to date with the earlier panels of this window, then factor it

@@ -483,58 +483,110 @@ Topology build_topology(int pairing, int n) {
 
 namespace msfec {
 
-DirectPlan build_direct_plan(const Topology &t) {
+DirectPlan build_direct_plan(const Topology &t, int ordering) {
   DirectPlan P;
   const int n = t.n, NI0 = t.blk[0].n_int;
   const int NI1 = t.two_blocks ? t.blk[1].n_int : 0;
   constexpr int PW = DirectPlan::kPanel;
-  auto slab_of = [&](int blk, int dof) {
+  // block key along z in elimination order: layer k -> 2k, plane k -> 2k-1 (split) ; slab -> ceil(z)-1
+  auto key_of = [&](int blk, int dof) {
     const double z = t.blk[blk].pos[3 * dof + 2];
-    int s = (int)std::ceil(z) - 1;
-    return std::min(std::max(s, 0), n - 1);
+    if (ordering == 1) return std::min(std::max((int)std::ceil(z) - 1, 0), n - 1);
+    const bool on_plane = (z == std::floor(z));
+    const int kz = (int)std::floor(z);
+    return on_plane ? 2 * kz - 1 : 2 * kz;
   };
-  // members of each slab: sigma-type first, then u-type (interior DoFs only)
-  std::vector<std::vector<int>> members(n);   // stacked interior row index
-  for (int d = 0; d < NI0; ++d) members[slab_of(0, d)].push_back(d);
-  for (int d = 0; d < NI1; ++d) members[slab_of(1, d)].push_back(NI0 + d);
-  // RT_DQ: the system has the constant-u null space (rt_dq_basis.cc:683-709); fix the last
-  // u DoF of the last slab to zero.  sigma is unaffected, u is overwritten by 1 afterwards.
-  if (t.pairing == MSFEC_RT_DQ) P.pinned_row = members[n - 1].back();
-  // drop empty slabs (Q: slab n-1 holds no interior vertex)
+  std::map<int, std::vector<int>> by_key;   // stacked interior row indices, sigma-type first
+  for (int d = 0; d < NI0; ++d) by_key[key_of(0, d)].push_back(d);
+  for (int d = 0; d < NI1; ++d) by_key[key_of(1, d)].push_back(NI0 + d);
   std::vector<std::vector<int>> slabs;
-  for (auto &m : members) if (!m.empty()) slabs.push_back(m);
-  P.n_slabs = (int)slabs.size();
-  P.bs.resize(P.n_slabs); P.slab_off.resize(P.n_slabs); P.ld.resize(P.n_slabs); P.col_off.resize(P.n_slabs);
+  for (auto &kv : by_key) slabs.push_back(kv.second);
+  // Padding-aware balancing: a block whose size exceeds a multiple of 32 by a few DoFs hands its last
+  // u-type DoFs to the next block if they fit into that block's padding (n = 8 Ned_RT: layers 161 -> 160).
+  // Deferring u-type DoFs keeps every leading matrix non-singular (the leading Schur complement only loses
+  // rows/columns), so the no-pivot factorisation is unaffected.
+  for (size_t s = 0; s + 1 < slabs.size(); ++s) {
+    const int excess = (int)slabs[s].size() % PW;
+    const int next_fill = (int)slabs[s + 1].size() % PW;
+    int n_u = 0;
+    for (int r : slabs[s]) n_u += r >= NI0;
+    const bool u_block = t.two_blocks;
+    if (!u_block || excess == 0 || excess > 8 || n_u < excess) continue;
+    if (next_fill == 0 || next_fill + excess > PW) continue;
+    for (int q = 0; q < excess; ++q) { slabs[s + 1].push_back(slabs[s].back()); slabs[s].pop_back(); }
+  }
+  // RT_DQ: the system has the constant-u null space (rt_dq_basis.cc:683-709); fix the last u DoF of the
+  // last block to zero.  sigma is unaffected, u is overwritten by 1 afterwards.
+  if (t.pairing == MSFEC_RT_DQ) P.pinned_row = slabs.back().back();
+  const int nB = (int)slabs.size();
+  P.n_slabs = nB;
+  P.bs.resize(nB); P.slab_off.resize(nB); P.ld.resize(nB); P.col_off.resize(nB); P.front_rows.resize(nB);
   int off = 0;
-  for (int s = 0; s < P.n_slabs; ++s) {
+  for (int s = 0; s < nB; ++s) {
     P.bs[s] = ((int)slabs[s].size() + PW - 1) / PW * PW;
     P.slab_off[s] = off;
     off += P.bs[s];
   }
   P.NP = off;
-  int64_t boff = 0;
-  for (int s = 0; s < P.n_slabs; ++s) {
-    P.ld[s] = P.bs[s] + (s + 1 < P.n_slabs ? P.bs[s + 1] : 0) + DirectPlan::kRhsRows;
-    P.col_off[s] = boff;
-    boff += (int64_t)P.ld[s] * P.bs[s];
-  }
-  P.band_doubles = boff;
-  if (boff >= (int64_t)1 << 31) throw std::runtime_error("direct solver band exceeds 2^31 entries per cell");
   P.perm.assign(t.NI, -1); P.inv_perm.assign(P.NP, -1);
-  std::vector<int> slab_of_p(P.NP, 0);
-  for (int s = 0; s < P.n_slabs; ++s) {
+  std::vector<int> blk_of_p(P.NP, 0);
+  for (int s = 0; s < nB; ++s) {
     for (int i = 0; i < (int)slabs[s].size(); ++i) {
       P.perm[slabs[s][i]] = P.slab_off[s] + i;
       P.inv_perm[P.slab_off[s] + i] = slabs[s][i];
     }
-    for (int i = 0; i < P.bs[s]; ++i) slab_of_p[P.slab_off[s] + i] = s;
+    for (int i = 0; i < P.bs[s]; ++i) blk_of_p[P.slab_off[s] + i] = s;
   }
-  auto dest_of = [&](int pr, int pc) -> int64_t {   // lower entry (pr >= pc)
-    const int s = slab_of_p[pc];
-    if (slab_of_p[pr] != s && slab_of_p[pr] != s + 1) throw std::runtime_error("direct plan: matrix is not block tridiagonal");
-    return P.col_off[s] + (int64_t)(pc - P.slab_off[s]) * P.ld[s] + (pr - P.slab_off[s]);
-  };
+  // block graph + symbolic factorisation
   const RefOperator &S = t.sys;
+  std::vector<std::vector<char>> adj(nB, std::vector<char>(nB, 0));
+  auto couple = [&](int r, int c) {
+    const int a = blk_of_p[P.perm[r]], b = blk_of_p[P.perm[c]];
+    if (a != b) adj[std::min(a, b)][std::max(a, b)] = 1;
+  };
+  for (int r = 0; r < S.n_rows; ++r) {
+    for (int e = S.cptr[r]; e < S.cptr[r + 1]; ++e) couple(r, S.ccol[e]);
+    for (int e = S.sptr[r]; e < S.sptr[r + 1]; ++e) couple(r, S.scol[e]);
+  }
+  std::vector<std::vector<int>> reach(nB);
+  for (int s = 0; s < nB; ++s) {
+    for (int b = s + 1; b < nB; ++b) if (adj[s][b]) reach[s].push_back(b);
+    for (size_t i = 0; i < reach[s].size(); ++i)
+      for (size_t j = i + 1; j < reach[s].size(); ++j) adj[reach[s][i]][reach[s][j]] = 1;
+  }
+  // fronts, chunk tables, band layout
+  P.front_pos.assign((size_t)nB * nB, -1);
+  P.chunk_off.assign(1, 0);
+  int64_t boff = 0;
+  for (int s = 0; s < nB; ++s) {
+    int rows = 0;
+    std::vector<int> front = {s};
+    front.insert(front.end(), reach[s].begin(), reach[s].end());
+    for (int b : front) {
+      P.front_pos[(size_t)s * nB + b] = rows;
+      for (int i = 0; i < P.bs[b]; i += PW) { P.chunk_blk.push_back(b); P.chunk_local.push_back(i); }
+      rows += P.bs[b];
+    }
+    P.chunk_blk.push_back(-1); P.chunk_local.push_back(0);   // the rhs chunk
+    P.chunk_off.push_back((int32_t)P.chunk_blk.size());
+    P.front_rows[s] = rows;
+    P.ld[s] = rows + DirectPlan::kRhsRows;
+    P.col_off[s] = boff;
+    boff += (int64_t)P.ld[s] * P.bs[s];
+    // flops of the right-looking trailing updates of this block column (lower triangle of what lies behind each panel)
+    for (int j0 = 0; j0 < P.bs[s]; j0 += PW) {
+      const double R = P.ld[s] - (j0 + PW), Cn = rows - (j0 + PW);
+      if (Cn > 0) P.update_flops += 2.0 * PW * (Cn * R - Cn * (Cn - 1) / 2.0);
+    }
+  }
+  P.band_doubles = boff;
+  if (boff >= (int64_t)1 << 31) throw std::runtime_error("direct solver band exceeds 2^31 entries per cell");
+  auto dest_of = [&](int pr, int pc) -> int64_t {   // lower entry (pr >= pc)
+    const int c = blk_of_p[pc], r = blk_of_p[pr];
+    const int fp = P.front_pos[(size_t)c * nB + r];
+    if (fp < 0) throw std::runtime_error("direct plan: entry outside the symbolic block structure");
+    return P.col_off[c] + (int64_t)(pc - P.slab_off[c]) * P.ld[c] + fp + (pr - P.slab_off[r]);
+  };
   for (int r = 0; r < S.n_rows; ++r) {
     const int pr = P.perm[r];
     for (int e = S.cptr[r]; e < S.cptr[r + 1]; ++e) {
@@ -556,8 +608,8 @@ DirectPlan build_direct_plan(const Topology &t) {
   P.rhs_dest.assign(t.NI, -1);
   for (int r = 0; r < t.NI; ++r) {
     if (r == P.pinned_row) continue;
-    const int p = P.perm[r], s = slab_of_p[p];
-    P.rhs_dest[r] = (int32_t)(P.col_off[s] + (int64_t)(p - P.slab_off[s]) * P.ld[s] + (P.ld[s] - DirectPlan::kRhsRows));
+    const int p = P.perm[r], s = blk_of_p[p];
+    P.rhs_dest[r] = (int32_t)(P.col_off[s] + (int64_t)(p - P.slab_off[s]) * P.ld[s] + P.front_rows[s]);
   }
   if (P.pinned_row >= 0) P.inv_perm[P.perm[P.pinned_row]] = -1;   // solution there stays 0
   return P;

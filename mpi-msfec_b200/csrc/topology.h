@@ -77,22 +77,32 @@ struct Topology {
 // ---------------------------------------------------------------------------------------
 // Plan of the batched direct solver ("use direct solver basis = true", reference
 // solve_direct, ned_rt_basis.cc:579-634).  The interior saddle system is symmetric in the
-// form [A00 -K^T; -K -A11].  Interior DoFs are grouped into z-slabs: slab s = DoFs of fine-cell
-// layer s plus the DoFs on the plane above it (ceil(z)-1), sigma-type DoFs first, then u-type,
-// padded to a multiple of 32 with identity pivots.  Cells in layer s only touch slabs s-1 and
-// s, so the matrix is block tridiagonal, and every leading principal block is a well-posed
-// sub-box problem with essential conditions on the cut, so an LDL^T factorisation WITHOUT
-// pivoting exists (positive pivots for sigma-type, negative for u-type DoFs).
-// Storage per cell ("band"): block column s is a column-major (ld_s x bs_s) panel whose rows
-// are [slab s | slab s+1 | 32 right-hand-side rows]; the k right-hand sides ride along as
-// extra rows so the forward substitution is part of the factorisation.
+// form [A00 -K^T; -K -A11].  Interior DoFs are grouped into BLOCKS along z, eliminated in order:
+//   "split" (default): layer 0, plane 1, layer 1, plane 2, ...  (DoFs inside a fine-cell layer /
+//                      DoFs lying on the plane between two layers)
+//   "slab":            layer k together with the plane above it
+// sigma-type DoFs first inside a block, padded to a multiple of 32 with identity pivots.  Every
+// leading set of blocks is a sub-box problem with essential conditions on the cut, so an LDL^T
+// factorisation WITHOUT pivoting exists (positive pivots on sigma-type, negative on u-type DoFs;
+// DESIGN.md).  A symbolic factorisation on the block graph gives, for every block column s, the
+// list of later blocks it reaches (its "front": a layer reaches the plane above it; a plane reaches
+// the next layer and the next plane).  Storage per cell ("band"): block column s is a column-major
+// (ld_s x bs_s) panel whose rows are [block s | reached blocks ... | 32 right-hand-side rows]; the
+// k right-hand sides ride along as extra rows so the forward substitution is part of the
+// factorisation.
 struct DirectPlan {
   static constexpr int kPanel = 32;     // panel width == padding granularity
   static constexpr int kRhsRows = 32;   // rhs rows per block column (k <= 20 used)
-  int n_slabs = 0, NP = 0;              // NP = padded number of unknowns
-  std::vector<int32_t> bs, slab_off, ld;      // per slab (bs/ld padded), slab_off in padded numbering
+  int n_slabs = 0, NP = 0;              // number of blocks; NP = padded number of unknowns
+  std::vector<int32_t> bs, slab_off, ld;      // per block (bs/ld padded), slab_off in padded numbering
+  std::vector<int32_t> front_rows;            // ld - kRhsRows: DoF rows of the front of block column s
   std::vector<int64_t> col_off;               // offset (doubles) of block column s inside a cell's band
   int64_t band_doubles = 0;
+  // front structure in 32-row chunks: chunk t of block column s covers front rows [32t, 32t+32)
+  std::vector<int32_t> chunk_off;             // [n_slabs+1]
+  std::vector<int32_t> chunk_blk;             // block the chunk belongs to
+  std::vector<int32_t> chunk_local;           // row offset of the chunk inside that block
+  std::vector<int32_t> front_pos;             // [n_slabs*n_slabs] front row offset of block b in column c, -1 if absent
   std::vector<int32_t> perm;                  // interior row (stacked numbering) -> padded index
   std::vector<int32_t> inv_perm;              // padded index -> interior row or -1 (padding / pinned)
   std::vector<int32_t> cell_dest, cell_ref;   // fill list, per-cell slot entries (lower triangle)
@@ -102,11 +112,13 @@ struct DirectPlan {
   std::vector<double> const_val;
   std::vector<int32_t> rhs_dest;              // [NI] band offset of rhs row 0 of this DoF's column (-1: pinned)
   int pinned_row = -1;                        // RT_DQ: u DoF fixed to 0 (constant null space)
+  double update_flops = 0;                    // FP64 flops of all trailing updates per cell (lower triangle)
 };
 
 // Builds everything above.  pairing: enum msfec_pairing; n = 2^L.
 Topology build_topology(int pairing, int n);
-DirectPlan build_direct_plan(const Topology &t);
+// ordering: 0 = split layers/planes (default), 1 = slabs
+DirectPlan build_direct_plan(const Topology &t, int ordering = 0);
 
 // Quadrature abscissae of QGauss<3>(2) on the unit cube, x fastest.
 void gauss_points(double qp[8][3]);
