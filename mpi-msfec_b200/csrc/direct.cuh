@@ -137,10 +137,6 @@ k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off,
 }
 
 // ---- trailing update on FP64 tensor cores ----------------------------------------------
-__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");

@@ -167,6 +167,11 @@ __global__ void k_build_precond(int NI0, int NI, int n_slots, const int *__restr
 
 constexpr int kMaxK = 20;
 
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
 // b = F1 * f1scale + Lift * G  for all k right-hand sides.  grid (ceil(NI/4), groups), block (32, 4)
 __global__ void k_lift_rhs(OpDev L, int NI, int NB, int k, int n_slots, double kscale, double f1scale,
                            const double *__restrict__ vals, const double *__restrict__ G,
@@ -394,6 +399,42 @@ k_minres_wx(MinresDev M, const double *__restrict__ V, double *__restrict__ w1, 
   }
 }
 
+// True residual of the interior systems: per cell max_j ||b_j - Sys x_j||_inf and max_j ||b_j||_inf (atomicMax on
+// the bit patterns of non-negative doubles).  grid (ceil(NI/8), groups), block (32, 8)
+__global__ void k_residual(OpDev S, int NI, int k, int n_slots, double kscale, const double *__restrict__ vals,
+                           const double *__restrict__ x, const double *__restrict__ b, int skip_row,
+                           unsigned long long *__restrict__ rmax, unsigned long long *__restrict__ bmax) {
+  const int lane = threadIdx.x, g = blockIdx.y;
+  const int row = blockIdx.x * blockDim.y + threadIdx.y;
+  if (row >= NI || row == skip_row) return;
+  const double *v = vals + (size_t)g * n_slots * kLanes + lane;
+  double acc[kMaxK];
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) acc[j] = j < k ? b[(((size_t)g * NI + row) * k + j) * kLanes + lane] : 0.0;
+  double bm = 0.0;
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) bm = fmax(bm, fabs(acc[j]));
+  for (int e = S.cptr[row]; e < S.cptr[row + 1]; ++e) {
+    const int ref = S.cref[e];
+    double a = v[(size_t)(ref >> 1) * kLanes];
+    if (ref & 1) a = -a;
+    const double *xc = x + ((size_t)g * NI + S.ccol[e]) * k * kLanes + lane;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < k) acc[j] = fma(-a, xc[j * kLanes], acc[j]);
+  }
+  for (int e = S.sptr[row]; e < S.sptr[row + 1]; ++e) {
+    const double a = S.sval[e] * kscale;
+    const double *xc = x + ((size_t)g * NI + S.scol[e]) * k * kLanes + lane;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j < k) acc[j] = fma(-a, xc[j * kLanes], acc[j]);
+  }
+  double rm = 0.0;
+#pragma unroll
+  for (int j = 0; j < kMaxK; ++j) rm = fmax(rm, fabs(acc[j]));
+  atomicMax(&rmax[g * kLanes + lane], (unsigned long long)__double_as_longlong(rm));
+  atomicMax(&bmax[g * kLanes + lane], (unsigned long long)__double_as_longlong(bm));
+}
+
 // number of still-active columns (cells beyond n_valid are ignored)
 __global__ void k_count_active(MinresDev M, int groups, int n_valid, int *out) {
   const int lane = threadIdx.x, j = threadIdx.y, g = blockIdx.x;
@@ -458,23 +499,104 @@ __global__ void k_apply_full(OpDev A, int NF, int kg, int n_slots, double kscale
   for (int j = 0; j < kMaxK; ++j) if (j < kg) Y[(((size_t)g * NF + row) * kg + j) * kLanes + lane] = acc[j];
 }
 
-// M[cell][i][j] = sum_d Z[d][i] Y[d][j] ;  r[cell][i] = sum_{d in rhs block} Z[d][i] grhs[d]
-// grid (kg, groups), block (32, kg)
-__global__ void k_gram(int NF, int kg, const double *__restrict__ Z, int gz0, const double *__restrict__ Y,
-                       const double *__restrict__ grhs, int rhs_off, int n_rhs, int cell0, int n_cells,
-                       double *__restrict__ Mout, double *__restrict__ rout) {
-  const int lane = threadIdx.x, j = threadIdx.y, i = blockIdx.x, g = blockIdx.y;
-  const double *z = Z + (((size_t)(gz0 + g) * NF) * kg + i) * kLanes + lane;
-  const double *y = Y + (((size_t)g * NF) * kg + j) * kLanes + lane;
-  double acc = 0.0;
-  for (int d = 0; d < NF; ++d) acc = fma(z[(size_t)d * kg * kLanes], y[(size_t)d * kg * kLanes], acc);
-  const int cell = cell0 + g * kLanes + lane;
-  if (cell < n_cells) Mout[((size_t)cell * kg + i) * kg + j] = acc;
-  if (j == 0) {
-    double r = 0.0;
-    for (int d = 0; d < n_rhs; ++d)
-      r = fma(z[(size_t)(rhs_off + d) * kg * kLanes], grhs[((size_t)g * n_rhs + d) * kLanes + lane], r);
-    if (cell < n_cells) rout[(size_t)cell * kg + i] = r;
+// Coarse element matrix M[cell] = Z^T Y (k x NF x k per cell) on the FP64 tensor cores, and the coarse rhs
+// r[cell][i] = sum_{d in rhs block} Z[d][i] grhs[d]  (assemble_global_element_matrix, ned_rt_basis.cc:850-948).
+// Z and Y are cell-interleaved ([d][j][32 cells]); a CTA owns one group of 32 cells and one slice of the d range,
+// stages tiles of 8 fine DoFs through shared memory transposed to per-cell [d][j] panels (odd cell stride: the
+// transposing stores are 2-way conflicted at worst) and each of its 8 warps runs the 24x24 (3x3 m8n8k4 tiles)
+// product of 4 cells.  Slices are summed by k_gram_reduce, so the result is deterministic.
+// grid (groups, n_slices), block 256
+constexpr int kGramDT = 8;                     // fine DoFs per staged tile
+constexpr int kGramJ = 24;                     // k padded to 3 MMA tiles
+constexpr int kGramCS = kGramDT * kGramJ + 1;  // per-cell stride in shared memory (odd)
+__global__ void __launch_bounds__(256)
+k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double *__restrict__ Y,
+            const double *__restrict__ grhs, int rhs_off, int n_rhs, int n_slices,
+            double *__restrict__ Mpart, double *__restrict__ rpart) {
+  extern __shared__ double gram_smem[];
+  double *Zs = gram_smem, *Ys = gram_smem + kLanes * kGramCS;
+  const int g = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int per = ((NF + n_slices - 1) / n_slices + kGramDT - 1) / kGramDT * kGramDT;
+  const int d_lo = slice * per, d_hi = min(NF, d_lo + per);
+  const double *z = Z + (size_t)(gz0 + g) * NF * kg * kLanes;
+  const double *y = Y + (size_t)g * NF * kg * kLanes;
+  double acc[4][3][3][2];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) acc[c][a][b][0] = acc[c][a][b][1] = 0.0;
+  double racc = 0.0;                                       // rhs: thread (cell = lane, i = warp + 8*q) handled below
+  for (int idx = tid; idx < kLanes * kGramCS; idx += 256) { Zs[idx] = 0.0; Ys[idx] = 0.0; }   // zero the j padding once
+  __syncthreads();
+  for (int d0 = d_lo; d0 < d_hi; d0 += kGramDT) {
+    // stage: element (dd, j, cell) ; consecutive threads -> consecutive cells (coalesced 256 B global reads)
+    for (int idx = tid; idx < kGramDT * kg * kLanes; idx += 256) {
+      const int cell = idx & 31, t = idx >> 5, j = t % kg, dd = t / kg;
+      const bool ok = d0 + dd < d_hi;
+      const size_t o = ((size_t)(d0 + dd) * kg + j) * kLanes + cell;
+      Zs[cell * kGramCS + dd * kGramJ + j] = ok ? z[o] : 0.0;
+      Ys[cell * kGramCS + dd * kGramJ + j] = ok ? y[o] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const double *zc = Zs + (warp + 8 * c) * kGramCS, *yc = Ys + (warp + 8 * c) * kGramCS;
+#pragma unroll
+      for (int ks = 0; ks < kGramDT / 4; ++ks) {
+        double af[3], bf[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+          af[t] = zc[(ks * 4 + fk) * kGramJ + t * 8 + fr];       // A[m = i][k = d] = Z[d][i]
+          bf[t] = yc[(ks * 4 + fk) * kGramJ + t * 8 + fr];       // B[k = d][n = j] = Y[d][j]
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+          for (int b = 0; b < 3; ++b) dmma_m8n8k4(acc[c][a][b][0], acc[c][a][b][1], af[a], bf[b]);
+      }
+    }
+    __syncthreads();
+  }
+  // partial M: Mpart[slice][cell in batch][24][24]
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    double *mp = Mpart + (((size_t)slice * gridDim.x + g) * kLanes + warp + 8 * c) * kGramJ * kGramJ;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) mp[(a * 8 + fr) * kGramJ + b * 8 + fk * 2 + h] = acc[c][a][b][h];
+  }
+  // coarse rhs (tiny): thread (lane = cell, i = warp + 8 q), slice of the rhs block rows
+  for (int i = warp; i < kg; i += 8) {
+    racc = 0.0;
+    for (int d = max(d_lo, rhs_off); d < min(d_hi, rhs_off + n_rhs); ++d)
+      racc = fma(z[((size_t)d * kg + i) * kLanes + lane], grhs[((size_t)g * n_rhs + d - rhs_off) * kLanes + lane], racc);
+    rpart[(((size_t)slice * gridDim.x + g) * kLanes + lane) * kGramJ + i] = racc;
+  }
+}
+
+// sum the slices in a fixed order.  grid (ceil(nb/4)), block (kGramJ*kGramJ?) -> one thread per (cell, i, j)
+__global__ void k_gram_reduce(int kg, int groups, int n_slices, int cell0, int n_cells, const double *__restrict__ Mpart,
+                              const double *__restrict__ rpart, double *__restrict__ Mout, double *__restrict__ rout) {
+  const int c = blockIdx.x;                      // cell inside the batch
+  const int cell = cell0 + c;
+  if (cell >= n_cells) return;
+  for (int e = threadIdx.x; e < kg * kg + kg; e += blockDim.x) {
+    double s = 0.0;
+    if (e < kg * kg) {
+      const int i = e / kg, j = e % kg;
+      for (int sl = 0; sl < n_slices; ++sl) s += Mpart[((size_t)sl * groups * kLanes + c) * kGramJ * kGramJ + i * kGramJ + j];
+      Mout[((size_t)cell * kg + i) * kg + j] = s;
+    } else {
+      const int i = e - kg * kg;
+      for (int sl = 0; sl < n_slices; ++sl) s += rpart[((size_t)sl * groups * kLanes + c) * kGramJ + i];
+      rout[(size_t)cell * kg + i] = s;
+    }
   }
 }
 
@@ -581,6 +703,7 @@ class Engine {
     CUDA_OK(cudaMalloc(&d_flag_, 4 * sizeof(int)));
     CUDA_OK(cudaMallocHost(&h_flag_, 4 * sizeof(int)));
     n_slots_ = T_.n_slots0 + T_.n_slots1;
+    CUDA_OK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLanes * kGramCS * sizeof(double))));
     use_direct_ = spec_.p.use_direct_solver_basis != 0;
     if (const char *e = std::getenv("MSFEC_FORCE_SOLVER")) use_direct_ = std::string(e) == "direct";
     if (use_direct_) {
@@ -655,9 +778,11 @@ class Engine {
   double *d_x0_ = nullptr, *d_coef_ = nullptr, *d_fr_ = nullptr, *d_vals_ = nullptr, *d_grhs_ = nullptr, *d_minv_ = nullptr;
   long long *d_gid_ = nullptr;
   double *d_vec_[8]{};   // ra, rb, T, yp, V, wa, wb, x
-  double *d_sc_ = nullptr, *d_Y_ = nullptr;
+  double *d_sc_ = nullptr, *d_Y_ = nullptr, *d_gram_part_ = nullptr;
+  size_t gram_part_size_ = 0;
   // store for all cells of the last build
   int store_cells_ = 0, store_groups_ = 0;
+  unsigned long long *d_res_ = nullptr;
   double *d_Z_ = nullptr, *d_U_ = nullptr, *d_M_ = nullptr, *d_r_ = nullptr, *d_corners_ = nullptr, *d_w_ = nullptr;
   long long *d_ids_ = nullptr;
   bool have_weights_ = false;
@@ -684,7 +809,7 @@ class Engine {
 
 void Engine::free_batch() {
   cudaFree(d_x0_); cudaFree(d_coef_); cudaFree(d_fr_); cudaFree(d_vals_); cudaFree(d_grhs_); cudaFree(d_minv_);
-  cudaFree(d_gid_); cudaFree(d_sc_); cudaFree(d_Y_);
+  cudaFree(d_gid_); cudaFree(d_sc_); cudaFree(d_Y_); cudaFree(d_gram_part_); d_gram_part_ = nullptr; gram_part_size_ = 0;
   for (auto &p : d_vec_) { cudaFree(p); p = nullptr; }
   d_x0_ = d_coef_ = d_fr_ = d_vals_ = d_grhs_ = d_minv_ = d_sc_ = d_Y_ = nullptr; d_gid_ = nullptr;
   batch_groups_ = 0;
@@ -708,6 +833,7 @@ void Engine::alloc_batch(int groups) {
 }
 
 void Engine::free_store() {
+  cudaFree(d_res_); d_res_ = nullptr;
   cudaFree(d_Z_); cudaFree(d_U_); cudaFree(d_M_); cudaFree(d_r_); cudaFree(d_corners_); cudaFree(d_ids_); cudaFree(d_w_);
   d_Z_ = d_U_ = d_M_ = d_r_ = d_corners_ = d_w_ = nullptr; d_ids_ = nullptr;
   store_cells_ = store_groups_ = 0;
@@ -723,6 +849,7 @@ void Engine::alloc_store(int n_cells) {
   CUDA_OK(cudaMalloc(&d_r_, (size_t)n_cells * T_.k_gram * sizeof(double)));
   CUDA_OK(cudaMalloc(&d_corners_, (size_t)n_cells * 24 * sizeof(double)));
   CUDA_OK(cudaMalloc(&d_ids_, (size_t)n_cells * sizeof(long long)));
+  CUDA_OK(cudaMalloc(&d_res_, 2 * (size_t)groups * kLanes * sizeof(unsigned long long)));
   store_cells_ = n_cells; store_groups_ = groups;
 }
 
@@ -901,6 +1028,14 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       timed = false;
     }
   }
+  // verification: true residual of every cell (the lifted rhs b is still in d_vec_[2]); read back once per build
+  {
+    const size_t cap = (size_t)store_groups_ * kLanes;
+    unsigned long long *rmax = d_res_ + last_batch_cell0_, *bmax = d_res_ + cap + last_batch_cell0_;
+    k_residual<<<dim3((NI + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(sys_.dev, NI, k, n_slots_, kscale, d_vals_, d_vec_[7],
+                                                                          d_vec_[2], P_.pinned_row, rmax, bmax);
+    ++launches_;
+  }
   (void)st;
 }
 
@@ -939,6 +1074,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   const int batch_cells = std::min(n_cells, (cpb + kLanes - 1) / kLanes * kLanes);
   alloc_batch((batch_cells + kLanes - 1) / kLanes);
   CUDA_OK(cudaMemsetAsync(d_flag_, 0, 4 * sizeof(int), stream_));
+  CUDA_OK(cudaMemsetAsync(d_res_, 0, 2 * (size_t)store_groups_ * kLanes * sizeof(unsigned long long), stream_));
   float ms_asm = 0, ms_lift = 0, ms_solve = 0, ms_gram = 0;
   double ms_spmm = 0;
   long total_it = 0;
@@ -959,7 +1095,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     }
     k_assemble_slots<<<dim3((T_.asm_rhs.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
         asmrhs_.dev, T_.nC, d_fr_, std::pow(h, T_.asm_rhs.h_exponent) / 8.0, d_grhs_, T_.asm_rhs.n_slots, 0);
-    k_build_precond<<<dim3((T_.NI + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
+    if (!use_direct_) k_build_precond<<<dim3((T_.NI + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
         T_.blk[0].n_int, T_.NI, n_slots_, d_diag0_, d_diag1_, kint_.dev, kscale, d_vals_, d_minv_);
     CUDA_OK(cudaEventRecord(ev_[1], stream_));
     k_lift_rhs<<<dim3((T_.NI + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(
@@ -976,8 +1112,20 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     k_finalize_basis<<<dim3((T_.NF + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(D, d_vec_[7], d_G_, d_Z_, gz0);
     k_apply_full<<<dim3((T_.NF + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(full_.dev, T_.NF, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
     const int rhs_off = T_.rhs_block ? T_.blk[0].n_total : 0;
-    k_gram<<<dim3(kg, groups), dim3(kLanes, kg), 0, stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
-                                                            cell0, n_cells, d_M_, d_r_);
+    {
+      const int n_slices = std::max(1, std::min(16, (2 * 148 + groups - 1) / groups));
+      const size_t need = (size_t)n_slices * groups * kLanes * (kGramJ * kGramJ + kGramJ);
+      if (need > gram_part_size_) {
+        cudaFree(d_gram_part_);
+        CUDA_OK(cudaMalloc(&d_gram_part_, need * sizeof(double)));
+        gram_part_size_ = need;
+      }
+      double *Mpart = d_gram_part_, *rpart = d_gram_part_ + (size_t)n_slices * groups * kLanes * kGramJ * kGramJ;
+      k_gram_dmma<<<dim3(groups, n_slices), 256, 2 * kLanes * kGramCS * sizeof(double), stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
+                                                            n_slices, Mpart, rpart);
+      k_gram_reduce<<<nb, 128, 0, stream_>>>(kg, groups, n_slices, cell0, n_cells, Mpart, rpart, d_M_, d_r_);
+      ++launches_;
+    }
     launches_ += 3;
     CUDA_OK(cudaEventRecord(ev_[4], stream_));
     CUDA_OK(cudaStreamSynchronize(stream_));
@@ -1001,6 +1149,16 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   if (h_flag_[1]) throw std::invalid_argument("coarse cell " + std::to_string(h_flag_[1] - 1) +
                                               " is not an axis-aligned cube of the common edge length");
   if (h_flag_[2]) st.not_converged += 1;   // zero / non-finite pivot in the direct factorisation
+  if (use_direct_) {
+    const size_t cap = (size_t)store_groups_ * kLanes;
+    std::vector<double> h(2 * cap);
+    CUDA_OK(cudaMemcpy(h.data(), d_res_, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < n_cells; ++c) {
+      const double rel = h[cap + c] > 0 ? h[c] / h[cap + c] : 0.0;
+      st.residual_max = std::max(st.residual_max, rel);
+      if (!(rel <= 1e-6)) st.not_converged++;
+    }
+  }
   float ms_total;
   CUDA_OK(cudaEventElapsedTime(&ms_total, ev_[6], ev_[7]));
   st.iterations_mean /= std::max<double>(1.0, (double)n_cells * T_.k_solve);
