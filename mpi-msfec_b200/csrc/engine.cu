@@ -219,13 +219,13 @@ __device__ __forceinline__ double &SC(const MinresDev &M, int f, int g, int j, i
   return M.sc[(size_t)f * M.sc_stride + ((size_t)g * M.k + j) * kLanes + lane];
 }
 
-constexpr int kRW = 4;            // rows in flight per block (threadIdx.z)
+constexpr int kRW = 2;            // rows in flight per block (threadIdx.z)
 constexpr int kRowsPerBlock = 32; // rows handled by one block
 
 // Kernel A:  v = s*yp ;  T = Sys v - c1 r1 ;  alfa += v.T
 // grid (ceil(NI/kRowsPerBlock), groups), block (32, k/R, kRW)
 template <int R>
-__global__ void __launch_bounds__(32 * 5 * kRW)
+__global__ void __launch_bounds__(32 * 5 * kRW, 2)
 k_minres_spmm(MinresDev M, OpDev S, double kscale, const double *__restrict__ vals,
               const double *__restrict__ yp, const double *__restrict__ r1,
               double *__restrict__ V, double *__restrict__ T) {

@@ -20,7 +20,7 @@ namespace msfec {
 struct ParametersMs {          // subset of NedRT::ParametersMs the basis path reads
   msfec_problem problem{};
   std::string filename_output = "Ms", dirname_output = "data-output";
-  bool verbose = false, verbose_basis = false, prevent_output = false;
+  bool verbose = false, verbose_basis = false, prevent_output = false, write_first_basis = false;
   int n_refine_global = 2, n_refine_local = 1;
   // Reads the reference's .prm verbatim (ned_rt_parameters.cc:131-257).  Throws std::runtime_error.
   ParametersMs(const std::string &prm_filename, int pairing);
@@ -42,6 +42,11 @@ class BasisBatch {
   const double *rhs(int cell) const { return &r_[(size_t)cell * k_]; }
   void set_weights(int cell, const std::vector<double> &w);
   void fine_solution(int cell, std::vector<double> &b0, std::vector<double> &b1);
+  void basis_function(int cell, int index, std::vector<double> &b0, std::vector<double> &b1);
+  // VTU (ParaView) file of fine-grid data of one coarse cell: what output_global_solution_in_cell /
+  // output_basis write through deal.II DataOut (ned_rt_basis.cc:951-1031, 1092-1147).  Vector fields are
+  // written as cell data evaluated at the fine-cell centres, nodal fields as point data.
+  void write_vtu(int cell, const std::string &path, const std::vector<double> &b0, const std::vector<double> &b1);
   const msfec_stats &stats() const { return stats_; }
   int n_cells() const { return (int)ids_.size(); }
 
@@ -52,6 +57,9 @@ class BasisBatch {
   std::vector<double> corners_, M_, r_, w_;
   std::vector<int64_t> ids_;
   msfec_stats stats_{};
+  std::vector<double> pos_[2];
+  std::vector<int32_t> axis_[2];
+  void load_layout();
 };
 
 // Per-cell facade with the reference's interface.  Copyable before run(), like the reference

@@ -174,6 +174,16 @@ def test_cpp_host_driver(msfec, tmp_path):
     both = np.concatenate([got[0], got[1]])
     assert rel_err(both[:, :324], M) < 1e-12
     assert rel_err(both[:, 324:], bb.get_global_element_rhs()) < 1e-12
+    # "write first basis = true": 18 ParaView files of the first cell's basis functions
+    import xml.etree.ElementTree as ET
+    files = sorted((tmp_path / "out").glob("basis_Ned_RT.cell-0.index-*.vtu"))
+    assert len(files) == 18
+    piece = ET.parse(files[3]).getroot().find("UnstructuredGrid").find("Piece")
+    assert piece.get("NumberOfCells") == "64" and piece.get("NumberOfPoints") == "125"
+    names = [a.get("Name") for a in piece.find("CellData")]
+    assert names == ["sigma", "u", "div_u"]
+    sig = np.array(piece.find("CellData")[0].text.split(), float).reshape(64, 3)
+    assert np.isfinite(sig).all() and np.abs(sig).max() > 0
     # error path of the CLI
     r = subprocess.run([exe, "-x"], capture_output=True, text=True)
     assert r.returncode == 1
