@@ -718,6 +718,8 @@ class Engine {
       if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(4, std::atoi(w)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(4)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(4)));
+      for (auto &L : lane_) { CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
+      CUDA_OK(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&ev_timed_, cudaEventDisableTiming));
       ev_upd_.resize(2048);
       for (auto &ev : ev_upd_) CUDA_OK(cudaEventCreate(&ev));
     }
@@ -729,6 +731,9 @@ class Engine {
     cudaSetDevice(device_);
     free_batch(); free_store(); free_direct();
     for (auto &ev : ev_upd_) cudaEventDestroy(ev);
+    for (auto &L : lane_) { if (L.st) cudaStreamDestroy(L.st); if (L.done) cudaEventDestroy(L.done); }
+    if (ev_ready_) cudaEventDestroy(ev_ready_);
+    if (ev_timed_) cudaEventDestroy(ev_timed_);
     cudaFree(d_dp_front_); cudaFree(d_dp_choff_); cudaFree(d_dp_chblk_); cudaFree(d_dp_chloc_); cudaFree(d_dp_fpos_);
     cudaFree(d_dp_bs_); cudaFree(d_dp_off_); cudaFree(d_dp_ld_); cudaFree(d_dp_col_); cudaFree(d_dp_inv_);
     cudaFree(d_dp_cdest_); cudaFree(d_dp_cref_); cudaFree(d_dp_sdest_); cudaFree(d_dp_sval_); cudaFree(d_dp_kdest_);
@@ -798,7 +803,16 @@ class Engine {
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
       *d_dp_rhs_ = nullptr;
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
-  double *d_band_ = nullptr, *d_diagL_ = nullptr, *d_dvec_ = nullptr, *d_xT_ = nullptr;
+  // sub-batches are processed round-robin on kDirectLanes streams with private band storage, so the latency-bound
+  // phases of one sub-batch (diagonal blocks, panel solves, backward substitution, band memset) overlap with the
+  // compute-bound trailing updates of the other
+  static constexpr int kDirectLanes = 2;
+  struct DirectLane {
+    cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
+    double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr;
+  } lane_[kDirectLanes];
+  cudaEvent_t ev_ready_ = nullptr, ev_timed_ = nullptr;
   std::vector<cudaEvent_t> ev_upd_;
   double direct_flops_ = 0, direct_ms_update_ = 0, direct_flops_timed_ = 0;
   long direct_update_launches_ = 0;
@@ -927,25 +941,30 @@ int Engine::solve_batch(int groups, int n_valid, double kscale, msfec_stats &st,
 
 
 void Engine::free_direct() {
-  cudaFree(d_band_); cudaFree(d_diagL_); cudaFree(d_dvec_); cudaFree(d_xT_);
-  d_band_ = d_diagL_ = d_dvec_ = d_xT_ = nullptr; direct_sub_ = 0;
+  for (auto &L : lane_) {
+    cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT);
+    L.band = L.diagL = L.dvec = L.xT = nullptr;
+  }
+  direct_sub_ = 0;
 }
 
 void Engine::alloc_direct(int nb) {
-  // cells per sub-batch: bounded by a memory budget for the band (default 24 GB), multiple of 32
+  // cells per sub-batch: bounded by a memory budget for the bands of all lanes (default 24 GB), multiple of 32
   double budget_gb = 24.0;
   if (const char *e = std::getenv("MSFEC_DIRECT_BAND_GB")) budget_gb = std::atof(e);
-  long sub = (long)(budget_gb * 1e9 / ((double)P_.band_doubles * 8.0));
+  long sub = (long)(budget_gb * 1e9 / kDirectLanes / ((double)P_.band_doubles * 8.0));
   if (const char *e = std::getenv("MSFEC_DIRECT_BATCH")) sub = std::atol(e);
   sub = std::max(32L, sub / 32 * 32);
-  sub = std::min<long>(sub, (nb + 31) / 32 * 32);
+  sub = std::min<long>(sub, ((nb + kDirectLanes - 1) / kDirectLanes + 31) / 32 * 32);
   sub = std::min<long>(sub, 65535 / 32 * 32);
   if (sub <= direct_sub_) return;
   free_direct();
-  CUDA_OK(cudaMalloc(&d_band_, (size_t)sub * P_.band_doubles * sizeof(double)));
-  CUDA_OK(cudaMalloc(&d_diagL_, (size_t)sub * P_.NP * kDP * sizeof(double)));
-  CUDA_OK(cudaMalloc(&d_dvec_, (size_t)sub * P_.NP * sizeof(double)));
-  CUDA_OK(cudaMalloc(&d_xT_, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
+  for (auto &L : lane_) {
+    CUDA_OK(cudaMalloc(&L.band, (size_t)sub * P_.band_doubles * sizeof(double)));
+    CUDA_OK(cudaMalloc(&L.diagL, (size_t)sub * P_.NP * kDP * sizeof(double)));
+    CUDA_OK(cudaMalloc(&L.dvec, (size_t)sub * P_.NP * sizeof(double)));
+    CUDA_OK(cudaMalloc(&L.xT, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
+  }
   direct_sub_ = (int)sub;
 }
 
@@ -957,10 +976,17 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
   DirectPlanDev D{P_.n_slabs, NP, d_dp_bs_, d_dp_off_, d_dp_ld_, d_dp_front_, d_dp_col_, d_dp_choff_, d_dp_chblk_, d_dp_chloc_, d_dp_fpos_};
   bool timed = (direct_update_launches_ == 0);   // per-launch events on the first sub-batch of a build
   // equal-sized sub-batches (multiples of 32 cells) so that no ragged tail runs at low occupancy
-  const int n_sub = (nb + direct_sub_ - 1) / direct_sub_;
+  int n_sub = (nb + direct_sub_ - 1) / direct_sub_;
+  if (nb >= kDirectLanes * kLanes) n_sub = (n_sub + kDirectLanes - 1) / kDirectLanes * kDirectLanes;   // equal work per lane
   const int sub = std::min(direct_sub_, ((nb + n_sub - 1) / n_sub + kLanes - 1) / kLanes * kLanes);
-  for (int lo = 0; lo < nb; lo += sub) {
+  CUDA_OK(cudaEventRecord(ev_ready_, stream_));          // assembled values, lifted rhs and the cleared x are ready
+  for (auto &L : lane_) CUDA_OK(cudaStreamWaitEvent(L.st, ev_ready_, 0));
+  int i_sub = 0;
+  for (int lo = 0; lo < nb; lo += sub, ++i_sub) {
     const int hi = std::min(nb, lo + sub), nc = hi - lo;
+    DirectLane &L = lane_[i_sub % kDirectLanes];
+    cudaStream_t stream_ = L.st;                           // everything of this sub-batch goes to its lane
+    double *d_band_ = L.band, *d_diagL_ = L.diagL, *d_dvec_ = L.dvec, *d_xT_ = L.xT;
     const int g0 = lo / kLanes, ng = (hi + kLanes - 1) / kLanes - g0;
     CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
     const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
@@ -1019,6 +1045,9 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
     launches_ += 2;
     if (timed) {
+      // the event-bracketed sub-batch runs alone: the other lane starts after it
+      CUDA_OK(cudaEventRecord(ev_timed_, stream_));
+      for (auto &O : lane_) if (&O != &L) CUDA_OK(cudaStreamWaitEvent(O.st, ev_timed_, 0));
       CUDA_OK(cudaStreamSynchronize(stream_));
       for (size_t i = 0; i + 1 < ev_i + 1 && i / 2 < ev_flops.size(); i += 2) {
         float ms = 0;
@@ -1028,6 +1057,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       timed = false;
     }
   }
+  for (auto &L : lane_) { CUDA_OK(cudaEventRecord(L.done, L.st)); CUDA_OK(cudaStreamWaitEvent(stream_, L.done, 0)); }
   // verification: true residual of every cell (the lifted rhs b is still in d_vec_[2]); read back once per build
   {
     const size_t cap = (size_t)store_groups_ * kLanes;
