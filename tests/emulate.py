@@ -102,3 +102,49 @@ def emulate_cell(bb, prob, corners, cell_gid=0):
     off = N0 if D["rhs_block"] else 0
     r = Z[off:off + len(grhs)].T @ grhs
     return M, r, Z, dict(vals=vals, grhs=grhs, Sys=Sys, b=b, x=x)
+
+
+def emulate_direct(bb, vals, kscale, b):
+    """numpy model of the batched direct solver driven by the library's DirectPlan tables: fills the per-cell
+    'band' exactly like k_direct_fill_* (cell_dest/cell_ref, shared_dest/shared_val, const_dest/const_val,
+    rhs_dest), decodes it into the padded symmetric matrix through the front tables (col_off, ld, chunk_*),
+    runs a dense LDL^T WITHOUT pivoting in the padded elimination order and returns (x in interior numbering,
+    pivots d, padded->interior map)."""
+    bs = bb.table("direct.bs"); off = bb.table("direct.slab_off"); ld = bb.table("direct.ld")
+    col_off = bb.table("direct.col_off"); front_rows = bb.table("direct.front_rows")
+    ch_off = bb.table("direct.chunk_off"); ch_blk = bb.table("direct.chunk_blk"); ch_loc = bb.table("direct.chunk_local")
+    inv = bb.table("direct.inv_perm"); NP = len(inv); k = b.shape[1]
+    band = np.zeros(int(col_off[-1] + ld[-1] * bs[-1]))
+    cd = bb.table("direct.cell_dest"); cr = bb.table("direct.cell_ref")
+    band[cd] = np.where(cr & 1, -1.0, 1.0) * vals[cr >> 1]
+    sd = bb.table("direct.shared_dest")
+    if len(sd):
+        band[sd] = bb.table("direct.shared_val") * kscale
+    kd = bb.table("direct.const_dest")
+    if len(kd):
+        band[kd] = bb.table("direct.const_val")
+    rd = bb.table("direct.rhs_dest")
+    for r in range(len(rd)):
+        if rd[r] >= 0:
+            band[rd[r]:rd[r] + k] = b[r]
+    # decode band -> padded matrix A (lower) and rhs F
+    A = np.zeros((NP, NP)); F = np.zeros((NP, k))
+    for s in range(len(bs)):
+        P = band[col_off[s]: col_off[s] + ld[s] * bs[s]].reshape(bs[s], ld[s])      # [col][row] (column-major)
+        for t in range(ch_off[s], ch_off[s + 1]):
+            v0 = (t - ch_off[s]) * 32
+            if ch_blk[t] < 0:
+                F[off[s]: off[s] + bs[s], :] = P[:, v0: v0 + k]
+            else:
+                r0 = off[ch_blk[t]] + ch_loc[t]
+                A[r0: r0 + 32, off[s]: off[s] + bs[s]] = P[:, v0: v0 + 32].T
+    A = np.tril(A) + np.tril(A, -1).T
+    L = np.zeros_like(A); d = np.zeros(NP); W = A.copy()
+    for j in range(NP):
+        d[j] = W[j, j]; L[j:, j] = W[j:, j] / d[j]
+        W[j + 1:, j + 1:] -= np.outer(L[j + 1:, j], L[j + 1:, j]) * d[j]
+    xp = np.linalg.solve(L.T, np.linalg.solve(L, F) / d[:, None])
+    x = np.zeros_like(b)
+    real = inv >= 0
+    x[inv[real]] = xp[real]
+    return x, d, inv

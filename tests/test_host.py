@@ -124,3 +124,29 @@ def test_invalid_arguments(msfec):
     with pytest.raises(msfec.MsfecError) as e:
         msfec.BasisBuilder(p, device=-1)
     assert e.value.code == 7
+
+
+@pytest.mark.parametrize("pairing,L", [("Q", 2), ("Q_NED", 2), ("NED_RT", 2), ("RT_DQ", 2), ("NED_RT", 3)])
+def test_direct_plan_tables(msfec, pairing, L):
+    """The direct solver's host plan (block ordering, symbolic block structure, band fill lists): a numpy LDL^T
+    WITHOUT pivoting in the library's padded order reproduces the sparse-LU solution, pivots are positive on
+    sigma-type and negative on u-type unknowns (the existence argument of DESIGN.md), padding pivots are 1."""
+    seed = 20261017 if L == 3 else 0
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
+    cells = mo.morton_cells(2)
+    prob = oracle_problem(pairing, L, random_seed=seed)
+    M, r, Z, dbg = emulate.emulate_cell(bb, prob, cells[37], 37)
+    D = emulate.dims_of(bb)
+    h = (cells[37][7][0] - cells[37][0][0]) / D["n"]
+    x, d, inv = emulate.emulate_direct(bb, dbg["vals"], h ** D["k_h_exponent"], dbg["b"])
+    ref = dbg["x"]
+    sel = np.arange(D["NI0"]) if pairing == "RT_DQ" else np.arange(D["NI"])     # RT_DQ: u is fixed up to a constant
+    assert np.abs(x[sel] - ref[sel]).max() <= 1e-9 * np.abs(ref[sel]).max()
+    real = inv >= 0
+    is_u = np.zeros(len(inv), bool); is_u[real] = inv[real] >= D["NI0"]
+    assert (d[real & ~is_u] > 0).all() and (d[real & is_u] < 0).all()
+    pad = ~real
+    assert np.isin(d[pad], (1.0, -1.0)).all() and (d[pad] == -1.0).sum() == (1 if pairing == "RT_DQ" else 0)
+    # block structure sanity: every block column's front starts with itself; sizes are multiples of 32
+    bs = bb.table("direct.bs"); ch_off = bb.table("direct.chunk_off"); ch_blk = bb.table("direct.chunk_blk")
+    assert (bs % 32 == 0).all() and all(ch_blk[ch_off[s]] == s and ch_blk[ch_off[s + 1] - 1] == -1 for s in range(len(bs)))
