@@ -18,6 +18,7 @@ namespace msfec {
 namespace {
 
 constexpr int kDP = 32;   // panel width (DirectPlan::kPanel)
+constexpr int kMaxWindow = 4;   // panels per delayed update window
 
 // ---- fill ------------------------------------------------------------------------------
 // per-cell slot entries.  grid (ceil(ne/8), groups), block (32, 8); cell = g*32+lane
@@ -106,7 +107,8 @@ k_direct_diag(const double *__restrict__ band, size_t band_stride, long long col
 // grid (ceil(nrows/128), cells), block 128
 __global__ void __launch_bounds__(128)
 k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int pglob, int NP,
-               const double *__restrict__ diagL, const double *__restrict__ dvec) {
+               const double *__restrict__ diagL, const double *__restrict__ dvec, double *__restrict__ ybuf, int slot,
+               int ldy) {
   __shared__ double Ld[kDP][kDP + 1];
   __shared__ double dinv[kDP];
   const int cell = blockIdx.y, tid = threadIdx.x;
@@ -132,8 +134,14 @@ k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off,
     for (int q = 0; q < p; ++q) s = fma(-y[q], Ld[p][q], s);
     y[p] = s;
   }
+  // L = y D^-1 goes back in place; the trailing updates use C -= L (y)^T, so -y is kept in the window scratch
+  // (slot = position of this panel inside the current update window) to keep the MMA loop free of FP64 ALU work
+  double *Y = ybuf + ((size_t)cell * kMaxWindow + slot) * kDP * ldy;
 #pragma unroll
-  for (int p = 0; p < kDP; ++p) P[(size_t)(j0 + p) * ld + v] = y[p] * dinv[p];
+  for (int p = 0; p < kDP; ++p) {
+    P[(size_t)(j0 + p) * ld + v] = y[p] * dinv[p];
+    Y[(size_t)p * ldy + v] = -y[p];
+  }
 }
 
 // ---- trailing update on FP64 tensor cores ----------------------------------------------
@@ -147,14 +155,14 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // stage a TROWS-row x 32-column block of one source panel (global: column-major, rows contiguous) into
 // shared memory [p][i] with row stride TROWS+8; rows >= ld are zero-filled.  128 threads.
 template <int TROWS>
-__device__ __forceinline__ void stage_block(double *dst, const double *P, int ld, int jsrc, int row0, int tid) {
+__device__ __forceinline__ void stage_block(double *dst, const double *P, int ld, int n_rows, int jsrc, int row0, int tid) {
   constexpr int LDS = TROWS + 8, CPC = TROWS / 2;          // 16-byte chunks per column
 #pragma unroll
   for (int t = 0; t < CPC * kDP / 128; ++t) {
     const int chunk = tid + t * 128;
     const int p = chunk / CPC, i = (chunk % CPC) * 2;
     double *d = dst + p * LDS + i;
-    if (row0 + i < ld) cp_async16(d, P + (size_t)(jsrc + p) * ld + row0 + i);
+    if (row0 + i < n_rows) cp_async16(d, P + (size_t)(jsrc + p) * ld + row0 + i);
     else { d[0] = 0.0; d[1] = 0.0; }
   }
 }
@@ -169,7 +177,7 @@ struct DirectPlanDev {
 
 template <int TM, int TN>
 constexpr size_t update_smem_bytes(int max_src) {
-  return ((size_t)max_src * kDP * (TN + 8) + 2 * (size_t)kDP * (TM + 8) + (size_t)max_src * kDP) * sizeof(double);
+  return ((size_t)max_src * kDP * (TN + 8) + 2 * (size_t)kDP * (TM + 8)) * sizeof(double);
 }
 
 // C(vr, vc) -= sum_{p in source panels} L(vr, p) d_p L(vc, p) for target columns vc in [vc_lo, vc_hi) and
@@ -182,15 +190,14 @@ constexpr size_t update_smem_bytes(int max_src) {
 template <int TM, int TN>
 __global__ void __launch_bounds__(128)
 k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int vc_lo,
-                int vc_hi, const double *__restrict__ dvec) {
+                int vc_hi, const double *__restrict__ ybuf, int ldy) {
   constexpr int LDR = TM + 8, LDC = TN + 8, WN = TN / 32;
   extern __shared__ __align__(16) double upd_smem[];
   double *Lc = upd_smem;                                   // [nq][32][LDC]
   double *Lr = Lc + (size_t)nq * kDP * LDC;                // [2][32][LDR]
-  double *dsm = Lr + 2 * kDP * LDR;                        // [nq*32]
   const int tj = blockIdx.x, cell = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cbase = vc_lo + tj * TN;
-  const int ld = D.ld[s], front_rows = D.front_rows[s], NP = D.NP, pglob = D.slab_off[s] + jsrc;
+  const int ld = D.ld[s], front_rows = D.front_rows[s];
   const long long col_off = D.col_off[s];
   const int choff = D.chunk_off[s];
   double *cb = band + (size_t)cell * band_stride;
@@ -200,9 +207,10 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
   const int T = (ld - r_first + TM - 1) / TM;
   const int Z = gridDim.y;
   if ((int)blockIdx.y >= T) return;
-  for (int i = tid; i < nq * kDP; i += 128) dsm[i] = dvec[(size_t)cell * NP + pglob + i];
-  for (int q = 0; q < nq; ++q) stage_block<TN>(Lc + (size_t)q * kDP * LDC, P, ld, jsrc + q * kDP, cbase, tid);
-  stage_block<TM>(Lr, P, ld, jsrc, r_first + blockIdx.y * TM, tid);
+  // column operands: -y = -(L D) of the nq source panels, written by k_direct_panel into the window scratch
+  const double *Yc = ybuf + (size_t)cell * kMaxWindow * kDP * ldy;
+  for (int q = 0; q < nq; ++q) stage_block<TN>(Lc + (size_t)q * kDP * LDC, Yc + (size_t)q * kDP * ldy, ldy, ld, 0, cbase, tid);
+  stage_block<TM>(Lr, P, ld, ld, jsrc, r_first + blockIdx.y * TM, tid);
   cp_async_commit();
   const int wr = warp / WN, wc = warp % WN;
   const int fr = lane >> 2, fk = lane & 3;
@@ -228,7 +236,7 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
                     : D.front_pos[cblk * D.n_slabs + rb] + D.chunk_local[choff + (vr0 >> 5)];
     }
     // C is fetched into its own registers now and consumed after the MMAs, so its latency hides
-    // behind the nq source panels; the product is accumulated from zero with a negated A operand.
+    // behind the nq source panels; the product L (-y)^T is accumulated from zero.
     double acc[4][4][2], cold[4][4][2];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
@@ -245,24 +253,22 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
     }
     for (int q = 0; q < nq; ++q) {
       // prefetch the next (row tile, source panel) operand block
-      if (q + 1 < nq) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, jsrc + (q + 1) * kDP, rbase, tid);
-      else if (ti + Z < T) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, jsrc, rbase + Z * TM, tid);
+      if (q + 1 < nq) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc + (q + 1) * kDP, rbase, tid);
+      else if (ti + Z < T) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc, rbase + Z * TM, tid);
       cp_async_commit();
       cp_async_wait<1>();
       __syncthreads();
       if (active) {
         const double *A = Lr + buf * kDP * LDR + wr * 32 + fr;
         const double *B = Lc + (size_t)q * kDP * LDC + wc * 32 + fr;
-        const double *dq = dsm + q * kDP;
 #pragma unroll
         for (int ks = 0; ks < kDP / 4; ++ks) {
           const int kk = ks * 4 + fk;
-          const double dk = dq[kk];
           double af[4], bf[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            af[t] = -A[kk * LDR + t * 8];
-            bf[t] = B[kk * LDC + t * 8] * dk;
+            af[t] = A[kk * LDR + t * 8];
+            bf[t] = B[kk * LDC + t * 8];
           }
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt)

@@ -715,7 +715,8 @@ class Engine {
       d_dp_inv_ = dev_upload(P_.inv_perm); d_dp_cdest_ = dev_upload(P_.cell_dest); d_dp_cref_ = dev_upload(P_.cell_ref);
       d_dp_sdest_ = dev_upload(P_.shared_dest); d_dp_sval_ = dev_upload(P_.shared_val);
       d_dp_kdest_ = dev_upload(P_.const_dest); d_dp_kval_ = dev_upload(P_.const_val); d_dp_rhs_ = dev_upload(P_.rhs_dest);
-      if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(4, std::atoi(w)));
+      if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(kMaxWindow, std::atoi(w)));
+      for (int v : P_.ld) ldy_ = std::max(ldy_, v);
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(4)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(4)));
       for (auto &L : lane_) { CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
@@ -797,6 +798,7 @@ class Engine {
   bool use_direct_ = false;
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
   int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
+  int ldy_ = 0;                              // row stride of the window scratch (max front height)
   int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr, *d_dp_front_ = nullptr, *d_dp_choff_ = nullptr,
       *d_dp_chblk_ = nullptr, *d_dp_chloc_ = nullptr, *d_dp_fpos_ = nullptr;
   long long *d_dp_col_ = nullptr;
@@ -810,7 +812,7 @@ class Engine {
   struct DirectLane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
-    double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr;
+    double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr, *ybuf = nullptr;
   } lane_[kDirectLanes];
   cudaEvent_t ev_ready_ = nullptr, ev_timed_ = nullptr;
   std::vector<cudaEvent_t> ev_upd_;
@@ -942,8 +944,8 @@ int Engine::solve_batch(int groups, int n_valid, double kscale, msfec_stats &st,
 
 void Engine::free_direct() {
   for (auto &L : lane_) {
-    cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT);
-    L.band = L.diagL = L.dvec = L.xT = nullptr;
+    cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT); cudaFree(L.ybuf);
+    L.band = L.diagL = L.dvec = L.xT = L.ybuf = nullptr;
   }
   direct_sub_ = 0;
 }
@@ -964,6 +966,7 @@ void Engine::alloc_direct(int nb) {
     CUDA_OK(cudaMalloc(&L.diagL, (size_t)sub * P_.NP * kDP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.dvec, (size_t)sub * P_.NP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.xT, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
+    CUDA_OK(cudaMalloc(&L.ybuf, (size_t)sub * kMaxWindow * kDP * ldy_ * sizeof(double)));
   }
   direct_sub_ = (int)sub;
 }
@@ -986,7 +989,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     const int hi = std::min(nb, lo + sub), nc = hi - lo;
     DirectLane &L = lane_[i_sub % kDirectLanes];
     cudaStream_t stream_ = L.st;                           // everything of this sub-batch goes to its lane
-    double *d_band_ = L.band, *d_diagL_ = L.diagL, *d_dvec_ = L.dvec, *d_xT_ = L.xT;
+    double *d_band_ = L.band, *d_diagL_ = L.diagL, *d_dvec_ = L.dvec, *d_xT_ = L.xT, *d_ybuf_ = L.ybuf;
     const int g0 = lo / kLanes, ng = (hi + kLanes - 1) / kLanes - g0;
     CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
     const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
@@ -1010,12 +1013,12 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       if (strip) {
         const int T = (ld - vc_lo + 127) / 128;
         k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_dvec_);
+            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
       } else {
         const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 63) / 64;
         int Z = std::max(1, std::min(T, (4 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));   // aim at >= ~16 CTAs per SM
         k_direct_update<64, 64><<<dim3(Tc, Z, nc), 128, update_smem_bytes<64, 64>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_dvec_);
+            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
       }
       if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
       ++launches_; ++direct_update_launches_;
@@ -1034,7 +1037,8 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
           if (j > p0) launch_update(s, p0 * kDP, j - p0, j0, j0 + kDP, true);
           const int nrows = ld - (j0 + kDP);
           k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_flag_ + 2);
-          k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_);
+          k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_,
+                                                                             d_ybuf_, j - p0, ldy_);
           launches_ += 2;
         }
         // apply the whole window to everything behind it (rest of slab s, slab s+1, rhs rows)
