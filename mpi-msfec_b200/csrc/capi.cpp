@@ -208,7 +208,13 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
       // RT_DQ: a layer block alone is a pure-Neumann sub-problem (singular pivot); keep layer + plane together
       int ordering = p->pairing == MSFEC_RT_DQ ? 1 : 0;
       if (const char *e = std::getenv("MSFEC_DIRECT_ORDERING")) ordering = std::string(e) == "slab" ? 1 : ordering;
-      ctx->plan = build_direct_plan(ctx->topo, ordering);
+      try {
+        ctx->plan = build_direct_plan(ctx->topo, ordering);
+      } catch (const std::exception &) {
+        // only fatal if the direct path is requested (e.g. band > 2^31 entries per cell at 5+ local refinements)
+        if (p->use_direct_solver_basis) throw;
+        ctx->plan = DirectPlan();
+      }
     }
     if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan);
     *out = ctx;

@@ -18,7 +18,7 @@ namespace msfec {
 namespace {
 
 constexpr int kDP = 32;   // panel width (DirectPlan::kPanel)
-constexpr int kMaxWindow = 4;   // panels per delayed update window
+constexpr int kMaxWindow = 6;   // panels per delayed update window
 
 // ---- fill ------------------------------------------------------------------------------
 // per-cell slot entries.  grid (ceil(ne/8), groups), block (32, 8); cell = g*32+lane
@@ -153,13 +153,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // stage a TROWS-row x 32-column block of one source panel (global: column-major, rows contiguous) into
-// shared memory [p][i] with row stride TROWS+8; rows >= ld are zero-filled.  128 threads.
-template <int TROWS>
+// shared memory [p][i] with row stride TROWS+8; rows >= ld are zero-filled.  NT threads.
+template <int TROWS, int NT>
 __device__ __forceinline__ void stage_block(double *dst, const double *P, int ld, int n_rows, int jsrc, int row0, int tid) {
   constexpr int LDS = TROWS + 8, CPC = TROWS / 2;          // 16-byte chunks per column
 #pragma unroll
-  for (int t = 0; t < CPC * kDP / 128; ++t) {
-    const int chunk = tid + t * 128;
+  for (int t = 0; t < CPC * kDP / NT; ++t) {
+    const int chunk = tid + t * NT;
     const int p = chunk / CPC, i = (chunk % CPC) * 2;
     double *d = dst + p * LDS + i;
     if (row0 + i < n_rows) cp_async16(d, P + (size_t)(jsrc + p) * ld + row0 + i);
@@ -188,10 +188,10 @@ constexpr size_t update_smem_bytes(int max_src) {
 // the column operands of all source panels in shared memory and walks its row tiles with a cp.async
 // double buffer; the C tile is loaded straight into the DMMA accumulators.
 template <int TM, int TN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__((TM / 32) * (TN / 32) * 32)
 k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int vc_lo,
                 int vc_hi, const double *__restrict__ ybuf, int ldy) {
-  constexpr int LDR = TM + 8, LDC = TN + 8, WN = TN / 32;
+  constexpr int LDR = TM + 8, LDC = TN + 8, WN = TN / 32, NT = (TM / 32) * (TN / 32) * 32;
   extern __shared__ __align__(16) double upd_smem[];
   double *Lc = upd_smem;                                   // [nq][32][LDC]
   double *Lr = Lc + (size_t)nq * kDP * LDC;                // [2][32][LDR]
@@ -209,8 +209,8 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
   if ((int)blockIdx.y >= T) return;
   // column operands: -y = -(L D) of the nq source panels, written by k_direct_panel into the window scratch
   const double *Yc = ybuf + (size_t)cell * kMaxWindow * kDP * ldy;
-  for (int q = 0; q < nq; ++q) stage_block<TN>(Lc + (size_t)q * kDP * LDC, Yc + (size_t)q * kDP * ldy, ldy, ld, 0, cbase, tid);
-  stage_block<TM>(Lr, P, ld, ld, jsrc, r_first + blockIdx.y * TM, tid);
+  for (int q = 0; q < nq; ++q) stage_block<TN, NT>(Lc + (size_t)q * kDP * LDC, Yc + (size_t)q * kDP * ldy, ldy, ld, 0, cbase, tid);
+  stage_block<TM, NT>(Lr, P, ld, ld, jsrc, r_first + blockIdx.y * TM, tid);
   cp_async_commit();
   const int wr = warp / WN, wc = warp % WN;
   const int fr = lane >> 2, fk = lane & 3;
@@ -253,8 +253,8 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
     }
     for (int q = 0; q < nq; ++q) {
       // prefetch the next (row tile, source panel) operand block
-      if (q + 1 < nq) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc + (q + 1) * kDP, rbase, tid);
-      else if (ti + Z < T) stage_block<TM>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc, rbase + Z * TM, tid);
+      if (q + 1 < nq) stage_block<TM, NT>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc + (q + 1) * kDP, rbase, tid);
+      else if (ti + Z < T) stage_block<TM, NT>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc, rbase + Z * TM, tid);
       cp_async_commit();
       cp_async_wait<1>();
       __syncthreads();

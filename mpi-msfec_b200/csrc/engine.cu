@@ -706,6 +706,7 @@ class Engine {
     CUDA_OK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLanes * kGramCS * sizeof(double))));
     use_direct_ = spec_.p.use_direct_solver_basis != 0;
     if (const char *e = std::getenv("MSFEC_FORCE_SOLVER")) use_direct_ = std::string(e) == "direct";
+    if (use_direct_ && P_.n_slabs == 0) throw std::runtime_error("direct solver plan unavailable for this problem size");
     if (use_direct_) {
       d_dp_bs_ = dev_upload(P_.bs); d_dp_off_ = dev_upload(P_.slab_off); d_dp_ld_ = dev_upload(P_.ld);
       d_dp_front_ = dev_upload(P_.front_rows); d_dp_choff_ = dev_upload(P_.chunk_off); d_dp_chblk_ = dev_upload(P_.chunk_blk);
@@ -717,8 +718,10 @@ class Engine {
       d_dp_kdest_ = dev_upload(P_.const_dest); d_dp_kval_ = dev_upload(P_.const_val); d_dp_rhs_ = dev_upload(P_.rhs_dest);
       if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(kMaxWindow, std::atoi(w)));
       for (int v : P_.ld) ldy_ = std::max(ldy_, v);
-      CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(4)));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(4)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 64>(kMaxWindow)));
+      if (const char *b = std::getenv("MSFEC_DIRECT_BIG_TILES")) big_tiles_ = std::atoi(b) != 0;
       for (auto &L : lane_) { CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
       CUDA_OK(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&ev_timed_, cudaEventDisableTiming));
       ev_upd_.resize(2048);
@@ -799,6 +802,7 @@ class Engine {
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
   int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
   int ldy_ = 0;                              // row stride of the window scratch (max front height)
+  bool big_tiles_ = false;                   // window updates with 128x64 tiles / 8 warps
   int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr, *d_dp_front_ = nullptr, *d_dp_choff_ = nullptr,
       *d_dp_chblk_ = nullptr, *d_dp_chloc_ = nullptr, *d_dp_fpos_ = nullptr;
   long long *d_dp_col_ = nullptr;
@@ -1013,6 +1017,11 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       if (strip) {
         const int T = (ld - vc_lo + 127) / 128;
         k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
+            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
+      } else if (big_tiles_) {
+        const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 127) / 128;
+        int Z = std::max(1, std::min(T, (2 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));
+        k_direct_update<128, 64><<<dim3(Tc, Z, nc), 256, update_smem_bytes<128, 64>(nq), stream_>>>(
             d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
       } else {
         const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 63) / 64;
@@ -1270,7 +1279,10 @@ void engine_destroy(Engine *e) { delete e; }
   catch (const std::invalid_argument &ex) { err = ex.what(); return MSFEC_EINVAL; } \
   catch (const std::logic_error &ex) { err = ex.what(); return MSFEC_ESTATE; }      \
   catch (const std::bad_alloc &) { err = "out of host memory"; return MSFEC_ENOMEM; } \
-  catch (const std::exception &ex) { err = ex.what(); return MSFEC_ECUDA; }
+  catch (const std::exception &ex) {                                               \
+    err = ex.what();                                                               \
+    return err.find("out of memory") != std::string::npos ? MSFEC_ENOMEM : MSFEC_ECUDA; \
+  }
 
 int engine_build(Engine *e, int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix,
                  double *elem_rhs, bool device_ptrs, msfec_stats *stats, std::string &err) {
