@@ -84,12 +84,16 @@ __device__ __forceinline__ double ldl32_rows(double (&a)[kDP], int lane, int *ba
 }
 
 // Factor the 32x32 diagonal block at (j0, j0) of every cell: one warp per cell, publishes the unit-lower
-// factor (column-major, pivots on the diagonal) to diagL and the pivots to dvec.
+// factor (column-major, pivots on the diagonal) to diagL, the pivots to dvec and -- for the DMMA triangular
+// solves of k_direct_trsm -- the inverse V = L^-1 of the unit-lower factor (column-major) to vinv.
 // grid (ceil(cells/4)), block 128
 __global__ void __launch_bounds__(128)
 k_direct_diag(const double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int pglob, int NP,
-              int n_cells, double *__restrict__ diagL, double *__restrict__ dvec, int *__restrict__ bad) {
-  const int cell = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+              int n_cells, double *__restrict__ diagL, double *__restrict__ dvec, double *__restrict__ vinv,
+              int *__restrict__ bad) {
+  __shared__ double Ls[4][kDP][kDP + 1];
+  const int w = threadIdx.x >> 5;
+  const int cell = blockIdx.x * 4 + w, lane = threadIdx.x & 31;
   if (cell >= n_cells) return;
   const double *P = band + (size_t)cell * band_stride + col_off;
   double a[kDP];
@@ -100,22 +104,42 @@ k_direct_diag(const double *__restrict__ band, size_t band_stride, long long col
 #pragma unroll
   for (int p = 0; p < kDP; ++p) dl[(size_t)p * kDP + lane] = a[p];
   dvec[(size_t)cell * NP + pglob + lane] = di;
+  if (vinv == nullptr) return;
+  // V = L^-1: lane j solves L v = e_j (column j of V) by forward substitution; L(i, k) is a broadcast read
+#pragma unroll
+  for (int p = 0; p < kDP; ++p) Ls[w][lane][p] = (p < lane) ? a[p] : 0.0;
+  __syncwarp();
+  double v[kDP];
+#pragma unroll
+  for (int i = 0; i < kDP; ++i) {
+    double t = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < i; ++k) t = fma(-Ls[w][i][k], v[k], t);
+    v[i] = t;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kDP; ++i) Ls[w][i][lane] = v[i];          // Ls[i][j] = V(i, j)
+  __syncwarp();
+  double *vo = vinv + ((size_t)cell * NP + pglob) * kDP;
+#pragma unroll
+  for (int k = 0; k < kDP; ++k) vo[(size_t)k * kDP + lane] = Ls[w][lane][k];   // column-major: V(n = lane, k)
 }
 
 // Row-parallel triangular solve of the virtual rows v in [j0+32, ld) (rest of slab s, slab s+1 and the rhs
 // rows: forward substitution is fused into the factorisation) against the factored diagonal block.
 // grid (ceil(nrows/128), cells), block 128
 __global__ void __launch_bounds__(128)
-k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int pglob, int NP,
-               const double *__restrict__ diagL, const double *__restrict__ dvec, double *__restrict__ ybuf, int slot,
-               int ldy) {
+k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int row_hi, int j0, int pglob,
+               int NP, const double *__restrict__ diagL, const double *__restrict__ dvec, double *__restrict__ ybuf,
+               int slot, int ldy) {
   __shared__ double Ld[kDP][kDP + 1];
   __shared__ double dinv[kDP];
   const int cell = blockIdx.y, tid = threadIdx.x;
   double *P = band + (size_t)cell * band_stride + col_off;
   const int v = j0 + kDP + blockIdx.x * 128 + tid;
   double y[kDP];
-  if (v < ld) {
+  if (v < row_hi) {
 #pragma unroll
     for (int p = 0; p < kDP; ++p) y[p] = P[(size_t)(j0 + p) * ld + v];
   }
@@ -126,7 +150,7 @@ k_direct_panel(double *__restrict__ band, size_t band_stride, long long col_off,
   }
   if (tid < kDP) dinv[tid] = 1.0 / dvec[(size_t)cell * NP + pglob + tid];
   __syncthreads();
-  if (v >= ld) return;
+  if (v >= row_hi) return;
 #pragma unroll
   for (int p = 1; p < kDP; ++p) {
     double s = y[p];
@@ -189,8 +213,8 @@ constexpr size_t update_smem_bytes(int max_src) {
 // double buffer; the C tile is loaded straight into the DMMA accumulators.
 template <int TM, int TN>
 __global__ void __launch_bounds__((TM / 32) * (TN / 32) * 32)
-k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int vc_lo,
-                int vc_hi, const double *__restrict__ ybuf, int ldy) {
+k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int yslot0,
+                int vc_lo, int vc_hi, int row_hi, const double *__restrict__ ybuf, int ldy) {
   constexpr int LDR = TM + 8, LDC = TN + 8, WN = TN / 32, NT = (TM / 32) * (TN / 32) * 32;
   extern __shared__ __align__(16) double upd_smem[];
   double *Lc = upd_smem;                                   // [nq][32][LDC]
@@ -204,13 +228,13 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
   const double *P = cb + col_off;
   // row tiles of this CTA: rbase = r_first + (z + Z*i) * TM, first tile contains row cbase
   const int r_first = cbase - (cbase - vc_lo) % TM;        // TM-aligned relative to vc_lo
-  const int T = (ld - r_first + TM - 1) / TM;
+  const int T = (row_hi - r_first + TM - 1) / TM;   // rows >= row_hi are left alone (diagonal-region strips)
   const int Z = gridDim.y;
   if ((int)blockIdx.y >= T) return;
   // column operands: -y = -(L D) of the nq source panels, written by k_direct_panel into the window scratch
-  const double *Yc = ybuf + (size_t)cell * kMaxWindow * kDP * ldy;
-  for (int q = 0; q < nq; ++q) stage_block<TN, NT>(Lc + (size_t)q * kDP * LDC, Yc + (size_t)q * kDP * ldy, ldy, ld, 0, cbase, tid);
-  stage_block<TM, NT>(Lr, P, ld, ld, jsrc, r_first + blockIdx.y * TM, tid);
+  const double *Yc = ybuf + ((size_t)cell * kMaxWindow + yslot0) * kDP * ldy;
+  for (int q = 0; q < nq; ++q) stage_block<TN, NT>(Lc + (size_t)q * kDP * LDC, Yc + (size_t)q * kDP * ldy, ldy, row_hi, 0, cbase, tid);
+  stage_block<TM, NT>(Lr, P, ld, row_hi, jsrc, r_first + blockIdx.y * TM, tid);
   cp_async_commit();
   const int wr = warp / WN, wc = warp % WN;
   const int fr = lane >> 2, fk = lane & 3;
@@ -228,7 +252,7 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
   for (int ti = blockIdx.y; ti < T; ti += Z) {
     const int rbase = r_first + ti * TM;
     const int vr0 = rbase + wr * 32;
-    const bool active = col_ok && vr0 >= vc0 && vr0 < ld;
+    const bool active = col_ok && vr0 >= vc0 && vr0 < row_hi;
     int roff = vr0;
     if (active && cblk != s) {
       const int rb = D.chunk_blk[choff + (vr0 >> 5)];
@@ -253,8 +277,8 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
     }
     for (int q = 0; q < nq; ++q) {
       // prefetch the next (row tile, source panel) operand block
-      if (q + 1 < nq) stage_block<TM, NT>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc + (q + 1) * kDP, rbase, tid);
-      else if (ti + Z < T) stage_block<TM, NT>(Lr + (buf ^ 1) * kDP * LDR, P, ld, ld, jsrc, rbase + Z * TM, tid);
+      if (q + 1 < nq) stage_block<TM, NT>(Lr + (buf ^ 1) * kDP * LDR, P, ld, row_hi, jsrc + (q + 1) * kDP, rbase, tid);
+      else if (ti + Z < T) stage_block<TM, NT>(Lr + (buf ^ 1) * kDP * LDR, P, ld, row_hi, jsrc, rbase + Z * TM, tid);
       cp_async_commit();
       cp_async_wait<1>();
       __syncthreads();
@@ -288,6 +312,286 @@ k_direct_update(double *__restrict__ band, size_t band_stride, DirectPlanDev D, 
           for (int h = 0; h < 2; ++h)
             cdst[(size_t)(nt * 8 + fk * 2 + h) * ldc + roff + mt * 8 + fr] = cold[mt][nt][h] + acc[mt][nt][h];
     }
+  }
+  cp_async_wait<0>();
+}
+
+
+// ---- trailing update, streaming version -------------------------------------------------
+// Same operation as k_direct_update for large target regions: C(vr, vc) += sum_k L(vr, k) * Ys(vc, k) with
+// Ys = -(L D) from the window scratch (slots yslot0 .. yslot0+nq-1) and L from columns jsrc .. jsrc+32nq-1 of
+// block column s.  One 64x64 C tile per CTA (4 warps of 32x32), both operands streamed through a 4-stage
+// cp.async ring of K = 16 slices, so any K fits (the whole block column is applied to the reached blocks in
+// ONE pass: every C entry behind a block column is read and written once per block column, not once per
+// window).  The MMA m-dimension is the band COLUMN, so a thread's two accumulator entries are two
+// consecutive band rows: C moves with 16-byte accesses.  Shared-memory row stride 68 (= 4 mod 16) makes the
+// fragment loads conflict-free.
+// grid (tiles of the trapezoid vc in [vc_lo, vc_hi), vr in [vc, ld), cells); block 128.
+template <int TM, int TN, int KC, int ST>
+constexpr size_t update_s_smem() { return (size_t)ST * KC * (TM + 4 + TN + 4) * sizeof(double); }
+
+// number of tiles of the trapezoid (host side; the kernel decodes the same enumeration)
+template <int TM, int TN>
+inline int update_s_tiles(int ld, int vc_lo, int c_hi) {
+  int n = 0;
+  for (int cbase = vc_lo; cbase < c_hi; cbase += TN) {
+    const int r_first = cbase - (cbase - vc_lo) % TM;
+    n += (ld - r_first + TM - 1) / TM;
+  }
+  return n;
+}
+
+template <int TM, int TN, int KC, int ST, int MINB>
+__global__ void __launch_bounds__((TM / 32) * (TN / 32) * 32, MINB)
+k_direct_update_s(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int yslot0,
+                  int vc_lo, int vc_hi, const double *__restrict__ ybuf, int ldy) {
+  constexpr int NT = (TM / 32) * (TN / 32) * 32, LDL = TM + 4, LDY = TN + 4, STAGE = KC * (LDL + LDY);
+  constexpr int WC = TN / 32;
+  extern __shared__ __align__(16) double upd_smem[];
+  const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ld = D.ld[s], front_rows = D.front_rows[s];
+  // tile decode: column tile tc owns the row tiles from its own first row on (TM-aligned relative to vc_lo)
+  int cbase = vc_lo, rbase;
+  {
+    int t = blockIdx.x;
+    for (;; cbase += TN) {
+      const int r_first = cbase - (cbase - vc_lo) % TM;
+      const int T = (ld - r_first + TM - 1) / TM;
+      if (t < T) { rbase = r_first + t * TM; break; }
+      t -= T;
+    }
+  }
+  const long long col_off = D.col_off[s];
+  const int choff = D.chunk_off[s];
+  double *cb = band + (size_t)cell * band_stride;
+  const double *Lsrc = cb + col_off + (size_t)jsrc * ld;
+  const double *Ysrc = ybuf + ((size_t)cell * kMaxWindow + yslot0) * kDP * ldy;
+  const int nk = nq * (kDP / KC);
+  auto load_stage = [&](int kt) {
+    double *dst = upd_smem + (size_t)(kt % ST) * STAGE;
+#pragma unroll
+    for (int t = 0; t < KC * TM / 2 / NT; ++t) {
+      const int c = tid + t * NT;
+      const int k = c / (TM / 2), i = (c % (TM / 2)) * 2;
+      double *d = dst + k * LDL + i;
+      if (rbase + i < ld) cp_async16(d, Lsrc + (size_t)(kt * KC + k) * ld + rbase + i);
+      else { d[0] = 0.0; d[1] = 0.0; }
+    }
+#pragma unroll
+    for (int t = 0; t < KC * TN / 2 / NT; ++t) {
+      const int c = tid + t * NT;
+      const int k = c / (TN / 2), i = (c % (TN / 2)) * 2;
+      double *d = dst + KC * LDL + k * LDY + i;
+      if (cbase + i < ld) cp_async16(d, Ysrc + (size_t)(kt * KC + k) * ldy + cbase + i);
+      else { d[0] = 0.0; d[1] = 0.0; }
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < ST - 1; ++st) {
+    if (st < nk) load_stage(st);
+    cp_async_commit();
+  }
+  const int wr = warp / WC, wc = warp % WC;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int vc0 = cbase + wc * 32, vr0 = rbase + wr * 32;
+  const bool active = vc0 < vc_hi && vc0 < front_rows && vr0 >= vc0 && vr0 < ld;
+  double *cdst = cb;
+  int ldc = ld;
+  if (active) {
+    const int cblk = D.chunk_blk[choff + (vc0 >> 5)];
+    int roff = vr0;
+    if (cblk == s) cdst = cb + col_off + (size_t)vc0 * ld;
+    else {
+      ldc = D.ld[cblk];
+      cdst = cb + D.col_off[cblk] + (size_t)D.chunk_local[choff + (vc0 >> 5)] * ldc;
+      const int rb = D.chunk_blk[choff + (vr0 >> 5)];
+      roff = rb < 0 ? D.front_rows[cblk] + (vr0 - front_rows)
+                    : D.front_pos[cblk * D.n_slabs + rb] + D.chunk_local[choff + (vr0 >> 5)];
+    }
+    cdst += (size_t)fr * ldc + roff + fk * 2;
+  }
+  double acc[4][4][2];
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const double2 v = *reinterpret_cast<const double2 *>(cdst + (size_t)(mt * 8) * ldc + nt * 8);
+        acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
+      }
+  }
+  for (int kt = 0; kt < nk; ++kt) {
+    cp_async_wait<ST - 2>();
+    __syncthreads();
+    if (kt + ST - 1 < nk) load_stage(kt + ST - 1);
+    cp_async_commit();
+    if (active) {
+      const double *Ls = upd_smem + (size_t)(kt % ST) * STAGE + wr * 32 + fr;
+      const double *Ys = upd_smem + (size_t)(kt % ST) * STAGE + KC * LDL + wc * 32 + fr;
+#pragma unroll
+      for (int ks = 0; ks < KC / 4; ++ks) {
+        const int kk = ks * 4 + fk;
+        double af[4], bf[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          af[t] = Ys[kk * LDY + t * 8];
+          bf[t] = Ls[kk * LDL + t * 8];
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+      }
+    }
+  }
+  cp_async_wait<0>();
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        *reinterpret_cast<double2 *>(cdst + (size_t)(mt * 8) * ldc + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+  }
+}
+
+
+// ---- rows below a chunk: triangular solve on FP64 tensor cores ---------------------------
+// A chunk is np <= 6 consecutive panels (W = 32 np columns, first column jc0) of block column s whose W x W
+// diagonal region is already factored (sub-diagonal blocks L(p,q) in the band, V_p = L(p,p)^-1 in vinv, pivots
+// in dvec).  For the rows below it, A_rows = X L_dd^T with X = L_rows D, solved block-wise
+//   X_p = (A_p - sum_{q<p} X_q L(p,q)^T) V_p^T
+// entirely with mma.sync.m8n8k4.f64: the MMA m-dimension is the panel column, n the row, so accumulator pairs
+// are consecutive band rows (16-byte stores).  One CTA = 32 rows x W columns held in shared memory as
+// [column][row]; the 32x32 operand blocks L(p,q), V_p stream through a 3-stage cp.async ring.  Writes
+// L = X D^-1 in place and -X to the window scratch (slot p) for the chunk update.  Every band entry of these
+// rows is read once and written once (the 32-wide panel kernels moved it ~5 times).
+// grid ((ld - row_lo) / 32, cells), block 128 (warp = 16 columns x 16 rows of the current panel)
+constexpr int kTR = 32, kTLd = kTR + 4, kTBs = kDP + 4;
+constexpr size_t trsm_smem_bytes(int np) {
+  return ((size_t)np * kDP * kTLd + 3 * kDP * kTBs + kDP * kTLd + (size_t)np * kDP) * sizeof(double);
+}
+
+__global__ void __launch_bounds__(128)
+k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int jc0, int np, int row_lo,
+              int pglob0, int NP, const double *__restrict__ vinv, const double *__restrict__ dvec,
+              double *__restrict__ ybuf, int ldy) {
+  extern __shared__ __align__(16) double trsm_smem[];
+  double *Xs = trsm_smem;                                  // [32 np][kTLd]   A, then X
+  double *Bs = Xs + (size_t)np * kDP * kTLd;               // [3][32][kTBs]   operand ring, [k][n]
+  double *Ts = Bs + 3 * kDP * kTBs;                        // [32][kTLd]      T_p as MMA operand
+  double *dinv = Ts + kDP * kTLd;                          // [32 np]
+  const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = row_lo + blockIdx.x * kTR;
+  double *P = band + (size_t)cell * band_stride + col_off;
+  const int W = np * kDP;
+  // stage the A tile: W columns x 32 rows = 16 chunks of 16 bytes per column
+  for (int c = tid; c < W * (kTR / 2); c += 128) {
+    const int k = c / (kTR / 2), i = (c % (kTR / 2)) * 2;
+    cp_async16(Xs + k * kTLd + i, P + (size_t)(jc0 + k) * ld + r0 + i);
+  }
+  cp_async_commit();
+  for (int c = tid; c < W; c += 128) dinv[c] = 1.0 / dvec[(size_t)cell * NP + pglob0 + c];
+  const int nblk = np * (np + 1) / 2;
+  // block sequence: for p: L(p,0) .. L(p,p-1), V_p
+  auto stage_blk = [&](int b, int p, int q) {
+    double *dst = Bs + (size_t)(b % 3) * kDP * kTBs;
+    const double *src;
+    int lds;
+    if (q < p) { src = P + (size_t)(jc0 + q * kDP) * ld + jc0 + p * kDP; lds = ld; }
+    else { src = vinv + ((size_t)cell * NP + pglob0 + p * kDP) * kDP; lds = kDP; }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = tid + t * 128;
+      const int k = c >> 4, n = (c & 15) * 2;
+      cp_async16(dst + k * kTBs + n, src + (size_t)k * lds + n);
+    }
+  };
+  int sp = 0, sq = 0;                                      // (p, q) of the next block to stage
+  auto advance = [&](int &p, int &q) { if (q < p) ++q; else { ++p; q = 0; } };
+#pragma unroll
+  for (int b = 0; b < 2; ++b) {
+    if (b < nblk) { stage_blk(b, sp, sq); advance(sp, sq); }
+    cp_async_commit();
+  }
+  const int wm = warp >> 1, wn = warp & 1;                 // wm: column half (MMA m), wn: row half (MMA n)
+  const int fr = lane >> 2, fk = lane & 3;
+  double acc[2][2][2];
+  int p = 0, q = 0;
+  for (int b = 0; b < nblk; ++b) {
+    cp_async_wait<1>();
+    __syncthreads();
+    if (b + 2 < nblk) { stage_blk(b + 2, sp, sq); advance(sp, sq); }
+    cp_async_commit();
+    const double *Bb = Bs + (size_t)(b % 3) * kDP * kTBs + wm * 16 + fr;
+    if (q == 0 && p > 0) {
+      // acc := A_p (own 16 columns x 16 rows)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const double2 v = *reinterpret_cast<const double2 *>(Xs + (size_t)(p * kDP + wm * 16 + mt * 8 + fr) * kTLd + wn * 16 + nt * 8 + fk * 2);
+          acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
+        }
+    }
+    if (q < p) {
+      // acc -= L(p,q) X_q^T   (m = column of panel p, k = column of panel q, n = row)
+      const double *Xq = Xs + (size_t)(q * kDP) * kTLd + wn * 16 + fr;
+#pragma unroll
+      for (int ks = 0; ks < kDP / 4; ++ks) {
+        const int kk = ks * 4 + fk;
+        double af[2], bf[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { af[t] = -Bb[kk * kTBs + t * 8]; bf[t] = Xq[kk * kTLd + t * 8]; }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+      }
+      if (q == p - 1) {
+        // T_p complete: publish it as an MMA operand for the V_p product (visible after the next barrier)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+            *reinterpret_cast<double2 *>(Ts + (size_t)(wm * 16 + mt * 8 + fr) * kTLd + wn * 16 + nt * 8 + fk * 2) =
+                make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+      }
+    } else {
+      // X_p = V_p T_p  (m = column n' of panel p, k = column of T_p, n = row); for p = 0, T_0 = A_0 sits in Xs
+      const double *Tq = (p == 0 ? Xs : Ts) + wn * 16 + fr;
+      double x[2][2][2];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) x[mt][nt][0] = x[mt][nt][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < kDP / 4; ++ks) {
+        const int kk = ks * 4 + fk;
+        double af[2], bf[2];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) { af[t] = Bb[kk * kTBs + t * 8]; bf[t] = Tq[kk * kTLd + t * 8]; }
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(x[mt][nt][0], x[mt][nt][1], af[mt], bf[nt]);
+      }
+      if (p == 0) __syncthreads();                         // everyone has read A_0 before it is overwritten by X_0
+      double *Y = ybuf + ((size_t)cell * kMaxWindow + p) * kDP * ldy;
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int col = wm * 16 + mt * 8 + fr;             // column inside panel p
+        const double di = dinv[p * kDP + col];
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt) {
+          const int row = wn * 16 + nt * 8 + fk * 2;
+          const double x0 = x[mt][nt][0], x1 = x[mt][nt][1];
+          *reinterpret_cast<double2 *>(Xs + (size_t)(p * kDP + col) * kTLd + row) = make_double2(x0, x1);
+          *reinterpret_cast<double2 *>(P + (size_t)(jc0 + p * kDP + col) * ld + r0 + row) = make_double2(x0 * di, x1 * di);
+          *reinterpret_cast<double2 *>(Y + (size_t)col * ldy + r0 + row) = make_double2(-x0, -x1);
+        }
+      }
+    }
+    advance(p, q);
   }
   cp_async_wait<0>();
 }
@@ -378,6 +682,173 @@ k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPla
       }
       __syncthreads();
     }
+  }
+}
+
+
+// ---- backward substitution, block-column version ----------------------------------------
+// L^T x = z, one block column at a time (last to first), two launches per block column:
+//  k_direct_back_gemm   T = z - L(rows below the block, block columns)^T x(front)  for all 32-column panels of
+//                       the block column in parallel: grid (bs/32, cells).  The K = front rows below the block
+//                       stream through a 4-stage cp.async ring of 32-row slices, so the band is read at HBM
+//                       speed with long contiguous runs (the per-cell persistent kernel above is latency bound).
+//  k_direct_back_diag   x = L_dd^-T T inside the diagonal region: one warp per cell, panels last to first,
+//                       x_p = V_p^T (T_p - sum_{q>p} L(q,p)^T x_q), all products on mma.sync.m8n8k4.f64.
+// xT[cell][j][NP] holds T between the two launches and x afterwards.
+constexpr int kBLd = kDP + 4, kBStages = 4;
+constexpr size_t kBackGemmSmem = (size_t)kBStages * (kDP + 24) * kBLd * sizeof(double);
+
+__global__ void __launch_bounds__(128)
+k_direct_back_gemm(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int k, double *xT) {
+  extern __shared__ __align__(16) double bg_smem[];        // [stage][32 cols + 24 rhs][kBLd]
+  const int cell = blockIdx.y, j0 = blockIdx.x * kDP, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s], choff = D.chunk_off[s], rows_dof = D.front_rows[s];
+  const int NP = D.NP;
+  const double *P = band + (size_t)cell * band_stride + D.col_off[s];
+  double *x = xT + (size_t)cell * k * NP;
+  const int nst = (rows_dof - bs) / kDP;                   // 32-row slices below the block
+  // rhs rows >= k of every stage stay zero
+  for (int i = tid; i < kBStages * 24 * kBLd; i += 128) {
+    const int st = i / (24 * kBLd), r = i % (24 * kBLd);
+    if (r / kBLd >= k) bg_smem[(size_t)st * (kDP + 24) * kBLd + kDP * kBLd + r] = 0.0;
+  }
+  auto load_stage = [&](int t) {
+    double *dst = bg_smem + (size_t)(t % kBStages) * (kDP + 24) * kBLd;
+    const int i0 = bs + t * kDP;                           // first front row of the slice
+    const int ch = choff + (i0 >> 5);
+    const int xi = D.slab_off[D.chunk_blk[ch]] + D.chunk_local[ch];   // padded unknown index of that row
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int c = tid + u * 128;
+      const int col = c >> 4, i = (c & 15) * 2;
+      cp_async16(dst + col * kBLd + i, P + (size_t)(j0 + col) * ld + i0 + i);
+    }
+    for (int c = tid; c < k * 16; c += 128) {
+      const int j = c >> 4, i = (c & 15) * 2;
+      cp_async16(dst + (kDP + j) * kBLd + i, x + (size_t)j * NP + xi + i);
+    }
+  };
+#pragma unroll
+  for (int t = 0; t < kBStages - 1; ++t) {
+    if (t < nst) load_stage(t);
+    cp_async_commit();
+  }
+  double acc[3][2];
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
+  for (int t = 0; t < nst; ++t) {
+    cp_async_wait<kBStages - 2>();
+    __syncthreads();
+    if (t + kBStages - 1 < nst) load_stage(t + kBStages - 1);
+    cp_async_commit();
+    const double *Ls = bg_smem + (size_t)(t % kBStages) * (kDP + 24) * kBLd + (warp * 8 + fr) * kBLd;
+    const double *Xs = bg_smem + (size_t)(t % kBStages) * (kDP + 24) * kBLd + (kDP + fr) * kBLd;
+#pragma unroll
+    for (int ks = 0; ks < kDP / 4; ++ks) {
+      const double a = Ls[ks * 4 + fk];                    // A[m = column][k = row] = L(row, column)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) dmma_m8n8k4(acc[nt][0], acc[nt][1], a, Xs[nt * 8 * kBLd + ks * 4 + fk]);
+    }
+  }
+  cp_async_wait<0>();
+  const int c = warp * 8 + fr;
+#pragma unroll
+  for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int j = nt * 8 + fk * 2 + h;
+      if (j < k) x[(size_t)j * NP + so + j0 + c] = P[(size_t)(j0 + c) * ld + rows_dof + j] - acc[nt][h];
+    }
+}
+
+// grid (ceil(cells/4)), block 128 (warp per cell).  from_z: the block column has no rows below it (T = z).
+__global__ void __launch_bounds__(128)
+k_direct_back_diag(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int k, int n_cells,
+                   const double *__restrict__ vinv, int from_z, double *xT) {
+  __shared__ double ts[4][kDP][24 + 1];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * 4 + w;
+  if (cell >= n_cells) return;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s], rows_dof = D.front_rows[s], NP = D.NP;
+  const double *P = band + (size_t)cell * band_stride + D.col_off[s];
+  double *x = xT + (size_t)cell * k * NP;
+  const int np = bs / kDP;
+  for (int p = np - 1; p >= 0; --p) {
+    const int j0 = p * kDP;
+    double acc[4][3][2];
+    // t := T_p (m = column c, n = rhs j)
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c = mt * 8 + fr, j = nt * 8 + fk * 2 + h;
+          acc[mt][nt][h] = j < k ? (from_z ? P[(size_t)(j0 + c) * ld + rows_dof + j] : x[(size_t)j * NP + so + j0 + c]) : 0.0;
+        }
+    // t -= L(q,p)^T x_q for the panels q > p of this block column
+    for (int q = p + 1; q < np; ++q) {
+      const double *Lq = P + (size_t)(j0 + fr) * ld + q * kDP + fk;
+      const double *xq = x + (size_t)fr * NP + so + q * kDP + fk;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        double af[4][4], bf[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = (half * 4 + u) * 4;
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt) af[u][mt] = -Lq[(size_t)(mt * 8) * ld + r];
+#pragma unroll
+          for (int nt = 0; nt < 3; ++nt) bf[u][nt] = (nt * 8 + fr < k) ? xq[(size_t)(nt * 8) * NP + r] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[u][mt], bf[u][nt]);
+      }
+    }
+    // x_p = V_p^T t: t becomes the B operand through shared memory
+    __syncwarp();
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) ts[w][mt * 8 + fr][nt * 8 + fk * 2 + h] = acc[mt][nt][h];
+    __syncwarp();
+    double xo[4][3][2];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) xo[mt][nt][0] = xo[mt][nt][1] = 0.0;
+    const double *Vp = vinv + ((size_t)cell * NP + so + j0) * kDP;    // V(n, kk) at [kk * 32 + n]
+#pragma unroll
+    for (int ks = 0; ks < kDP / 4; ++ks) {
+      const int kk = ks * 4 + fk;
+      double af[4], bf[3];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) af[mt] = Vp[(size_t)(mt * 8 + fr) * kDP + kk];   // A[m = c][k = kk] = V(kk, c)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) bf[nt] = ts[w][kk][nt * 8 + fr];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt) dmma_m8n8k4(xo[mt][nt][0], xo[mt][nt][1], af[mt], bf[nt]);
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = nt * 8 + fk * 2 + h;
+          if (j < k) x[(size_t)j * NP + so + j0 + mt * 8 + fr] = xo[mt][nt][h];
+        }
+    __syncwarp();
   }
 }
 

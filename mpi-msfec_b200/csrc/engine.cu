@@ -27,6 +27,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
 #include <stdexcept>
 
 #include "engine.h"
@@ -720,8 +724,15 @@ class Engine {
       for (int v : P_.ld) ldy_ = std::max(ldy_, v);
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(kMaxWindow)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(kMaxWindow)));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 64>(kMaxWindow)));
-      if (const char *b = std::getenv("MSFEC_DIRECT_BIG_TILES")) big_tiles_ = std::atoi(b) != 0;
+      CUDA_OK(cudaFuncSetAttribute(k_direct_update_s<64, 64, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_s_smem<64, 64, 8, 4>()));
+      if (const char *b = std::getenv("MSFEC_DIRECT_CHUNK")) direct_chunk_ = std::max(1, std::min(kMaxWindow, std::atoi(b)));
+      if (const char *b = std::getenv("MSFEC_DIRECT_STREAM_UPDATE")) stream_update_ = std::atoi(b) != 0;
+      if (const char *b = std::getenv("MSFEC_DIRECT_TRSM")) use_trsm_ = std::atoi(b) != 0;
+      if (const char *b = std::getenv("MSFEC_DIRECT_BLOCK_BACKWARD")) block_backward_ = std::atoi(b) != 0;
+      CUDA_OK(cudaFuncSetAttribute(k_direct_back_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackGemmSmem));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes(kMaxWindow)));
+      if (!stream_update_) { direct_chunk_ = std::min(direct_chunk_, 4); use_trsm_ = false; }   // resident column operands: K <= 128
+      direct_window_ = std::min(direct_window_, direct_chunk_);
       for (auto &L : lane_) { CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
       CUDA_OK(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&ev_timed_, cudaEventDisableTiming));
       ev_upd_.resize(2048);
@@ -802,7 +813,10 @@ class Engine {
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
   int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
   int ldy_ = 0;                              // row stride of the window scratch (max front height)
-  bool big_tiles_ = false;                   // window updates with 128x64 tiles / 8 warps
+  int direct_chunk_ = 4;                     // panels per chunk (K = 32 * chunk for the update behind a chunk)
+  bool block_backward_ = true;               // backward substitution per block column (k_direct_back_gemm/_diag)
+  bool use_trsm_ = true;                     // rows below a chunk: one DMMA triangular solve (k_direct_trsm)
+  bool stream_update_ = true;                // k_direct_update_s (streamed operands) for window / chunk updates
   int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr, *d_dp_front_ = nullptr, *d_dp_choff_ = nullptr,
       *d_dp_chblk_ = nullptr, *d_dp_chloc_ = nullptr, *d_dp_fpos_ = nullptr;
   long long *d_dp_col_ = nullptr;
@@ -816,7 +830,7 @@ class Engine {
   struct DirectLane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
-    double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr, *ybuf = nullptr;
+    double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr, *ybuf = nullptr, *vinv = nullptr;
   } lane_[kDirectLanes];
   cudaEvent_t ev_ready_ = nullptr, ev_timed_ = nullptr;
   std::vector<cudaEvent_t> ev_upd_;
@@ -948,8 +962,8 @@ int Engine::solve_batch(int groups, int n_valid, double kscale, msfec_stats &st,
 
 void Engine::free_direct() {
   for (auto &L : lane_) {
-    cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT); cudaFree(L.ybuf);
-    L.band = L.diagL = L.dvec = L.xT = L.ybuf = nullptr;
+    cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT); cudaFree(L.ybuf); cudaFree(L.vinv);
+    L.band = L.diagL = L.dvec = L.xT = L.ybuf = L.vinv = nullptr;
   }
   direct_sub_ = 0;
 }
@@ -969,6 +983,7 @@ void Engine::alloc_direct(int nb) {
     CUDA_OK(cudaMalloc(&L.band, (size_t)sub * P_.band_doubles * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.diagL, (size_t)sub * P_.NP * kDP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.dvec, (size_t)sub * P_.NP * sizeof(double)));
+    CUDA_OK(cudaMalloc(&L.vinv, (size_t)sub * P_.NP * kDP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.xT, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.ybuf, (size_t)sub * kMaxWindow * kDP * ldy_ * sizeof(double)));
   }
@@ -993,75 +1008,147 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     const int hi = std::min(nb, lo + sub), nc = hi - lo;
     DirectLane &L = lane_[i_sub % kDirectLanes];
     cudaStream_t stream_ = L.st;                           // everything of this sub-batch goes to its lane
-    double *d_band_ = L.band, *d_diagL_ = L.diagL, *d_dvec_ = L.dvec, *d_xT_ = L.xT, *d_ybuf_ = L.ybuf;
+    double *d_band_ = L.band, *d_diagL_ = L.diagL, *d_dvec_ = L.dvec, *d_xT_ = L.xT, *d_ybuf_ = L.ybuf, *d_vinv_ = L.vinv;
     const int g0 = lo / kLanes, ng = (hi + kLanes - 1) / kLanes - g0;
+    // MSFEC_DIRECT_PROFILE=1: per-phase device times of the first sub-batch (events between the launches)
+    const bool prof = timed && std::getenv("MSFEC_DIRECT_PROFILE") != nullptr;
+    std::vector<std::pair<const char *, cudaEvent_t>> marks;
+    auto mark = [&](const char *tag) {
+      if (!prof) return;
+      cudaEvent_t e; CUDA_OK(cudaEventCreate(&e)); CUDA_OK(cudaEventRecord(e, stream_));
+      marks.emplace_back(tag, e);
+    };
+    mark("start");
     CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
+    mark("memset");
     const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
     k_direct_fill_cell<<<dim3((ne + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(ne, d_dp_cdest_, d_dp_cref_, d_vals_, n_slots_, g0, lo, hi, d_band_, stride);
     if (nes) k_direct_fill_shared<<<dim3((nes + 255) / 256, nc), 256, 0, stream_>>>(nes, d_dp_sdest_, d_dp_sval_, kscale, d_band_, stride);
     if (nek) k_direct_fill_shared<<<dim3((nek + 255) / 256, nc), 256, 0, stream_>>>(nek, d_dp_kdest_, d_dp_kval_, 1.0, d_band_, stride);
     k_direct_fill_rhs<<<dim3((NI + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(NI, k, d_dp_rhs_, d_vec_[2], g0, lo, hi, d_band_, stride);
     launches_ += 4;
+    mark("fill");
     size_t ev_i = 0;
     std::vector<double> ev_flops;
-    auto launch_update = [&](int s, int jsrc, int nq, int vc_lo, int vc_hi, bool strip) {
+    auto launch_update = [&](int s, int jsrc, int nq, int yslot0, int vc_lo, int vc_hi, bool strip, int row_hi = 0) {
       const int ld = P_.ld[s];
+      if (row_hi <= 0) row_hi = ld;
       const int c_hi = std::min(vc_hi, P_.front_rows[s]);
       if (c_hi <= vc_lo) return;
       // algorithmic flops: 2 * K * (entries vr >= vc of the target region)
-      const double R = ld - vc_lo, Cn = c_hi - vc_lo;
+      const double R = row_hi - vc_lo, Cn = c_hi - vc_lo;
       const double flops = 2.0 * kDP * nq * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
       direct_flops_ += flops;
       const bool tev = timed && ev_i + 2 <= ev_upd_.size();
       if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
       if (strip) {
-        const int T = (ld - vc_lo + 127) / 128;
+        const int T = (row_hi - vc_lo + 127) / 128;
         k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
-      } else if (big_tiles_) {
-        const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 127) / 128;
-        int Z = std::max(1, std::min(T, (2 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));
-        k_direct_update<128, 64><<<dim3(Tc, Z, nc), 256, update_smem_bytes<128, 64>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
-      } else {
+            d_band_, stride, D, s, jsrc, nq, yslot0, vc_lo, c_hi, row_hi, d_ybuf_, ldy_);
+      } else if (!stream_update_) {
         const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 63) / 64;
         int Z = std::max(1, std::min(T, (4 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));   // aim at >= ~16 CTAs per SM
         k_direct_update<64, 64><<<dim3(Tc, Z, nc), 128, update_smem_bytes<64, 64>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, vc_lo, c_hi, d_ybuf_, ldy_);
+            d_band_, stride, D, s, jsrc, nq, yslot0, vc_lo, c_hi, ld, d_ybuf_, ldy_);
+      } else {
+        k_direct_update_s<64, 64, 8, 4, 4><<<dim3(update_s_tiles<64, 64>(ld, vc_lo, c_hi), nc), 128, update_s_smem<64, 64, 8, 4>(), stream_>>>(
+            d_band_, stride, D, s, jsrc, nq, yslot0, vc_lo, c_hi, d_ybuf_, ldy_);
       }
       if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
       ++launches_; ++direct_update_launches_;
+      mark(strip ? "update strip" : vc_hi == (1 << 30) ? "update chunk" : "update window");
     };
     for (int s = 0; s < P_.n_slabs; ++s) {
       const int bs = P_.bs[s], ld = P_.ld[s];
       const int n_panels = bs / kDP;
-      // equal windows of at most direct_window_ panels (5 panels -> 3 + 2, 6 -> 3 + 3)
-      const int n_win = (n_panels + direct_window_ - 1) / direct_window_;
-      const int win = (n_panels + n_win - 1) / n_win;
-      for (int p0 = 0; p0 < n_panels; p0 += win) {
-        const int pe = std::min(n_panels, p0 + win);
-        for (int j = p0; j < pe; ++j) {
-          const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
-          // bring panel j up to date with the earlier panels of this window, then factor it
-          if (j > p0) launch_update(s, p0 * kDP, j - p0, j0, j0 + kDP, true);
-          const int nrows = ld - (j0 + kDP);
-          k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_flag_ + 2);
-          k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, d_diagL_, d_dvec_,
-                                                                             d_ybuf_, j - p0, ldy_);
-          launches_ += 2;
+      // CHUNKS of at most direct_chunk_ panels: a chunk is applied to everything behind it (rest of the block
+      // column, reached blocks, rhs rows) in one pass once it is complete.  Inside a chunk, equal WINDOWS of at
+      // most direct_window_ panels (5 panels -> 3 + 2): a window is applied to the rest of its chunk only.
+      const int n_chunk = (n_panels + direct_chunk_ - 1) / direct_chunk_;
+      const int chunk = (n_panels + n_chunk - 1) / n_chunk;
+      for (int c0 = 0; c0 < n_panels; c0 += chunk) {
+        const int c1 = std::min(n_panels, c0 + chunk);
+        if (use_trsm_) {
+          // (1) factor the diagonal region of the chunk (rows < 32 c1 only: small launches), (2) solve all rows
+          // below it in one pass on the tensor cores, (3) apply the chunk to everything behind it
+          const int row_hi = c1 * kDP;
+          for (int j = c0; j < c1; ++j) {
+            const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
+            if (j > c0) launch_update(s, c0 * kDP, j - c0, 0, j0, j0 + kDP, true, row_hi);
+            k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_vinv_, d_flag_ + 2);
+            ++launches_;
+            mark("diag");
+            const int nrows = row_hi - (j0 + kDP);
+            if (nrows > 0) {
+              k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, row_hi, j0, pglob, NP, d_diagL_,
+                                                                                 d_dvec_, d_ybuf_, j - c0, ldy_);
+              ++launches_;
+              mark("panel");
+            }
+          }
+          const int np = c1 - c0;
+          k_direct_trsm<<<dim3((ld - row_hi) / kTR, nc), 128, trsm_smem_bytes(np), stream_>>>(
+              d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+          ++launches_;
+          mark("trsm");
+          direct_flops_ += (double)(ld - row_hi) * (np * kDP) * ((np + 1) * kDP) * nc;   // 2 * rows * 32^2 * np(np+1)/2
+        } else {
+          const int n_win = (c1 - c0 + direct_window_ - 1) / direct_window_;
+          const int win = (c1 - c0 + n_win - 1) / n_win;
+          for (int p0 = c0; p0 < c1; p0 += win) {
+            const int pe = std::min(c1, p0 + win);
+            for (int j = p0; j < pe; ++j) {
+              const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
+              // bring panel j up to date with the earlier panels of this window, then factor it
+              if (j > p0) launch_update(s, p0 * kDP, j - p0, p0 - c0, j0, j0 + kDP, true);
+              const int nrows = ld - (j0 + kDP);
+              k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, nullptr, d_flag_ + 2);
+              k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, ld, j0, pglob, NP, d_diagL_, d_dvec_,
+                                                                                 d_ybuf_, j - c0, ldy_);
+              launches_ += 2;
+              mark("diag+panel");
+            }
+            // apply the window to the rest of its chunk
+            if (pe < c1) launch_update(s, p0 * kDP, pe - p0, p0 - c0, pe * kDP, c1 * kDP, false);
+          }
         }
-        // apply the whole window to everything behind it (rest of slab s, slab s+1, rhs rows)
-        launch_update(s, p0 * kDP, pe - p0, pe * kDP, 1 << 30, false);
+        // apply the whole chunk to everything behind it
+        launch_update(s, c0 * kDP, c1 - c0, 0, c1 * kDP, 1 << 30, false);
       }
     }
-    k_direct_backward<<<nc, 128, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);
+    if (block_backward_ && use_trsm_) {
+      for (int sb = P_.n_slabs - 1; sb >= 0; --sb) {
+        const bool below = P_.front_rows[sb] > P_.bs[sb];
+        if (below) k_direct_back_gemm<<<dim3(P_.bs[sb] / kDP, nc), 128, kBackGemmSmem, stream_>>>(d_band_, stride, D, sb, k, d_xT_);
+        k_direct_back_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, D, sb, k, nc, d_vinv_, below ? 0 : 1, d_xT_);
+        launches_ += below ? 2 : 1;
+      }
+    } else {
+      k_direct_backward<<<nc, 128, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);
+      ++launches_;
+    }
+    mark("backward");
     k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
-    launches_ += 2;
+    mark("scatter");
+    ++launches_;
     if (timed) {
       // the event-bracketed sub-batch runs alone: the other lane starts after it
       CUDA_OK(cudaEventRecord(ev_timed_, stream_));
       for (auto &O : lane_) if (&O != &L) CUDA_OK(cudaStreamWaitEvent(O.st, ev_timed_, 0));
       CUDA_OK(cudaStreamSynchronize(stream_));
+      if (prof) {
+        std::map<std::string, std::pair<double, int>> acc;
+        double total = 0;
+        for (size_t i = 1; i < marks.size(); ++i) {
+          float ms = 0;
+          CUDA_OK(cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second));
+          acc[marks[i].first].first += ms; acc[marks[i].first].second++; total += ms;
+        }
+        std::fprintf(stderr, "[msfec direct profile] sub-batch of %d cells, %.3f ms\n", nc, total);
+        for (auto &kv : acc)
+          std::fprintf(stderr, "  %-14s %5d launches %9.3f ms %5.1f%%\n", kv.first.c_str(), kv.second.second, kv.second.first, 100.0 * kv.second.first / total);
+        for (auto &m : marks) cudaEventDestroy(m.second);
+      }
       for (size_t i = 0; i + 1 < ev_i + 1 && i / 2 < ev_flops.size(); i += 2) {
         float ms = 0;
         CUDA_OK(cudaEventElapsedTime(&ms, ev_upd_[i], ev_upd_[i + 1]));
