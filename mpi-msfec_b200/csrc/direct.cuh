@@ -57,6 +57,46 @@ __global__ void k_direct_fill_rhs(int NI, int k, const int *__restrict__ rhs_des
   for (int j = 0; j < k; ++j) o[j] = b[(((size_t)g * NI + row) * k + j) * kLanes + lane];
 }
 
+// Fused zero + fill: every band entry is written exactly once (value or 0) with 16-byte stores, driven by
+// a per-entry code table shared by all cells (0: zero, 1: per-cell slot reference, 2: cell-independent value
+// x kscale, 3: constant, 4: right-hand side (row, j)).  Replaces memset + the four scatter kernels above
+// (whose 8-byte scattered writes cost a read-modify-write per sector).
+// grid (ceil(n_entries / 512), ceil(cells / 4)), block 256; band entries in pairs
+__device__ __forceinline__ double fill_value(int code, const double *__restrict__ vals_cell, const double *__restrict__ sval,
+                                             double kscale, const double *__restrict__ kval, const double *__restrict__ b_cell,
+                                             int k) {
+  const int t = code & 7, a = code >> 3;
+  if (t == 0) return 0.0;
+  if (t == 1) { const double v = vals_cell[(size_t)(a >> 1) * kLanes]; return (a & 1) ? -v : v; }
+  if (t == 2) return sval[a] * kscale;
+  if (t == 3) return kval[a];
+  return b_cell[((size_t)(a >> 5) * k + (a & 31)) * kLanes];
+}
+
+__global__ void __launch_bounds__(256)
+k_direct_fill_fused(const int2 *__restrict__ code, long long n_pairs, const double *__restrict__ vals, int n_slots,
+                    const double *__restrict__ sval, double kscale, const double *__restrict__ kval,
+                    const double *__restrict__ b, int NI, int k, int cell_lo, int n_cells, double *__restrict__ band,
+                    size_t band_stride) {
+  const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (e >= n_pairs) return;
+  const int2 c = code[e];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int ci = blockIdx.y * 4 + u;
+    if (ci >= n_cells) break;
+    double2 v = make_double2(0.0, 0.0);
+    if (c.x | c.y) {
+      const int cell = cell_lo + ci, g = cell / kLanes, lane = cell % kLanes;
+      const double *vc = vals + (size_t)g * n_slots * kLanes + lane;
+      const double *bc = b + (size_t)g * NI * k * kLanes + lane;
+      v.x = fill_value(c.x, vc, sval, kscale, kval, bc, k);
+      v.y = fill_value(c.y, vc, sval, kscale, kval, bc, k);
+    }
+    *reinterpret_cast<double2 *>(band + (size_t)ci * band_stride + 2 * e) = v;
+  }
+}
+
 // ---- panel factorisation ---------------------------------------------------------------
 // LDL^T of a 32x32 block held one row per lane (registers + shuffles, no shared-memory
 // round trips).  On return lane i holds row i of the unit-lower factor in a[0..i-1] and the

@@ -720,6 +720,18 @@ class Engine {
       d_dp_inv_ = dev_upload(P_.inv_perm); d_dp_cdest_ = dev_upload(P_.cell_dest); d_dp_cref_ = dev_upload(P_.cell_ref);
       d_dp_sdest_ = dev_upload(P_.shared_dest); d_dp_sval_ = dev_upload(P_.shared_val);
       d_dp_kdest_ = dev_upload(P_.const_dest); d_dp_kval_ = dev_upload(P_.const_val); d_dp_rhs_ = dev_upload(P_.rhs_dest);
+      if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_FILL")) fused_fill_ = std::atoi(b) != 0;
+      if (P_.band_doubles > (int64_t)8 << 20 || (P_.band_doubles & 1)) fused_fill_ = false;   // code table <= 32 MB
+      if (fused_fill_) {
+        std::vector<int32_t> code((size_t)P_.band_doubles, 0);
+        for (size_t e = 0; e < P_.cell_dest.size(); ++e) code[P_.cell_dest[e]] = (P_.cell_ref[e] << 3) | 1;
+        for (size_t e = 0; e < P_.shared_dest.size(); ++e) code[P_.shared_dest[e]] = ((int32_t)e << 3) | 2;
+        for (size_t e = 0; e < P_.const_dest.size(); ++e) code[P_.const_dest[e]] = ((int32_t)e << 3) | 3;
+        for (int r = 0; r < T_.NI; ++r)
+          if (P_.rhs_dest[r] >= 0)
+            for (int j = 0; j < T_.k_solve; ++j) code[P_.rhs_dest[r] + j] = ((r * 32 + j) << 3) | 4;
+        d_dp_code_ = dev_upload(code);
+      }
       if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(kMaxWindow, std::atoi(w)));
       for (int v : P_.ld) ldy_ = std::max(ldy_, v);
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(kMaxWindow)));
@@ -733,7 +745,19 @@ class Engine {
       CUDA_OK(cudaFuncSetAttribute(k_direct_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes(kMaxWindow)));
       if (!stream_update_) { direct_chunk_ = std::min(direct_chunk_, 4); use_trsm_ = false; }   // resident column operands: K <= 128
       direct_window_ = std::min(direct_window_, direct_chunk_);
-      for (auto &L : lane_) { CUDA_OK(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking)); CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)); }
+      if (const char *b = std::getenv("MSFEC_DIRECT_LANES")) kDirectLanes = std::max(1, std::min(kMaxDirectLanes, std::atoi(b)));
+      {
+        // MSFEC_DIRECT_PRIO=1: descending stream priorities (lane 0 highest), so the later lanes fill the gaps
+        int lo_p = 0, hi_p = 0;
+        CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));   // hi_p is numerically the smallest
+        const bool prio = std::getenv("MSFEC_DIRECT_PRIO") && std::atoi(std::getenv("MSFEC_DIRECT_PRIO")) != 0;
+        for (int i = 0; i < kDirectLanes; ++i) {
+          auto &L = lane_[i];
+          const int pr = prio ? std::min(lo_p, hi_p + i) : 0;
+          CUDA_OK(cudaStreamCreateWithPriority(&L.st, cudaStreamNonBlocking, pr));
+          CUDA_OK(cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming));
+        }
+      }
       CUDA_OK(cudaEventCreateWithFlags(&ev_ready_, cudaEventDisableTiming)); CUDA_OK(cudaEventCreateWithFlags(&ev_timed_, cudaEventDisableTiming));
       ev_upd_.resize(2048);
       for (auto &ev : ev_upd_) CUDA_OK(cudaEventCreate(&ev));
@@ -752,7 +776,7 @@ class Engine {
     cudaFree(d_dp_front_); cudaFree(d_dp_choff_); cudaFree(d_dp_chblk_); cudaFree(d_dp_chloc_); cudaFree(d_dp_fpos_);
     cudaFree(d_dp_bs_); cudaFree(d_dp_off_); cudaFree(d_dp_ld_); cudaFree(d_dp_col_); cudaFree(d_dp_inv_);
     cudaFree(d_dp_cdest_); cudaFree(d_dp_cref_); cudaFree(d_dp_sdest_); cudaFree(d_dp_sval_); cudaFree(d_dp_kdest_);
-    cudaFree(d_dp_kval_); cudaFree(d_dp_rhs_);
+    cudaFree(d_dp_kval_); cudaFree(d_dp_rhs_); cudaFree(d_dp_code_);
     sys_.release(); lift_.release(); full_.release(); kint_.release();
     asm00_.release(); asm11_.release(); asmrhs_.release();
     cudaFree(d_diag0_); cudaFree(d_diag1_); cudaFree(d_G_); cudaFree(d_F1_); cudaFree(d_prog_);
@@ -813,7 +837,7 @@ class Engine {
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
   int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
   int ldy_ = 0;                              // row stride of the window scratch (max front height)
-  int direct_chunk_ = 4;                     // panels per chunk (K = 32 * chunk for the update behind a chunk)
+  int direct_chunk_ = 3;                     // panels per chunk (K = 32 * chunk for the update behind a chunk)
   bool block_backward_ = true;               // backward substitution per block column (k_direct_back_gemm/_diag)
   bool use_trsm_ = true;                     // rows below a chunk: one DMMA triangular solve (k_direct_trsm)
   bool stream_update_ = true;                // k_direct_update_s (streamed operands) for window / chunk updates
@@ -821,17 +845,19 @@ class Engine {
       *d_dp_chblk_ = nullptr, *d_dp_chloc_ = nullptr, *d_dp_fpos_ = nullptr;
   long long *d_dp_col_ = nullptr;
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
-      *d_dp_rhs_ = nullptr;
+      *d_dp_rhs_ = nullptr, *d_dp_code_ = nullptr;
+  bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
   // sub-batches are processed round-robin on kDirectLanes streams with private band storage, so the latency-bound
   // phases of one sub-batch (diagonal blocks, panel solves, backward substitution, band memset) overlap with the
   // compute-bound trailing updates of the other
-  static constexpr int kDirectLanes = 2;
+  static constexpr int kMaxDirectLanes = 4;
+  int kDirectLanes = 2;                      // MSFEC_DIRECT_LANES (1..4)
   struct DirectLane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
     double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr, *ybuf = nullptr, *vinv = nullptr;
-  } lane_[kDirectLanes];
+  } lane_[kMaxDirectLanes];
   cudaEvent_t ev_ready_ = nullptr, ev_timed_ = nullptr;
   std::vector<cudaEvent_t> ev_upd_;
   double direct_flops_ = 0, direct_ms_update_ = 0, direct_flops_timed_ = 0;
@@ -979,7 +1005,8 @@ void Engine::alloc_direct(int nb) {
   sub = std::min<long>(sub, 65535 / 32 * 32);
   if (sub <= direct_sub_) return;
   free_direct();
-  for (auto &L : lane_) {
+  for (int i = 0; i < kDirectLanes; ++i) {
+    auto &L = lane_[i];
     CUDA_OK(cudaMalloc(&L.band, (size_t)sub * P_.band_doubles * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.diagL, (size_t)sub * P_.NP * kDP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.dvec, (size_t)sub * P_.NP * sizeof(double)));
@@ -1002,7 +1029,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
   if (nb >= kDirectLanes * kLanes) n_sub = (n_sub + kDirectLanes - 1) / kDirectLanes * kDirectLanes;   // equal work per lane
   const int sub = std::min(direct_sub_, ((nb + n_sub - 1) / n_sub + kLanes - 1) / kLanes * kLanes);
   CUDA_OK(cudaEventRecord(ev_ready_, stream_));          // assembled values, lifted rhs and the cleared x are ready
-  for (auto &L : lane_) CUDA_OK(cudaStreamWaitEvent(L.st, ev_ready_, 0));
+  for (int i = 0; i < kDirectLanes; ++i) CUDA_OK(cudaStreamWaitEvent(lane_[i].st, ev_ready_, 0));
   int i_sub = 0;
   for (int lo = 0; lo < nb; lo += sub, ++i_sub) {
     const int hi = std::min(nb, lo + sub), nc = hi - lo;
@@ -1019,13 +1046,20 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       marks.emplace_back(tag, e);
     };
     mark("start");
-    CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
-    mark("memset");
     const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
-    k_direct_fill_cell<<<dim3((ne + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(ne, d_dp_cdest_, d_dp_cref_, d_vals_, n_slots_, g0, lo, hi, d_band_, stride);
-    if (nes) k_direct_fill_shared<<<dim3((nes + 255) / 256, nc), 256, 0, stream_>>>(nes, d_dp_sdest_, d_dp_sval_, kscale, d_band_, stride);
-    if (nek) k_direct_fill_shared<<<dim3((nek + 255) / 256, nc), 256, 0, stream_>>>(nek, d_dp_kdest_, d_dp_kval_, 1.0, d_band_, stride);
-    k_direct_fill_rhs<<<dim3((NI + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(NI, k, d_dp_rhs_, d_vec_[2], g0, lo, hi, d_band_, stride);
+    if (fused_fill_) {
+      const long long n_pairs = (long long)(stride / 2);
+      k_direct_fill_fused<<<dim3((unsigned)((n_pairs + 255) / 256), (nc + 3) / 4), 256, 0, stream_>>>(
+          (const int2 *)d_dp_code_, n_pairs, d_vals_, n_slots_, d_dp_sval_, kscale, d_dp_kval_, d_vec_[2], NI, k, lo, nc, d_band_, stride);
+      launches_ -= 3;
+    } else {
+      CUDA_OK(cudaMemsetAsync(d_band_, 0, (size_t)nc * stride * sizeof(double), stream_));
+      mark("memset");
+      k_direct_fill_cell<<<dim3((ne + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(ne, d_dp_cdest_, d_dp_cref_, d_vals_, n_slots_, g0, lo, hi, d_band_, stride);
+      if (nes) k_direct_fill_shared<<<dim3((nes + 255) / 256, nc), 256, 0, stream_>>>(nes, d_dp_sdest_, d_dp_sval_, kscale, d_band_, stride);
+      if (nek) k_direct_fill_shared<<<dim3((nek + 255) / 256, nc), 256, 0, stream_>>>(nek, d_dp_kdest_, d_dp_kval_, 1.0, d_band_, stride);
+      k_direct_fill_rhs<<<dim3((NI + 7) / 8, ng), dim3(kLanes, 8), 0, stream_>>>(NI, k, d_dp_rhs_, d_vec_[2], g0, lo, hi, d_band_, stride);
+    }
     launches_ += 4;
     mark("fill");
     size_t ev_i = 0;
@@ -1134,7 +1168,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     if (timed) {
       // the event-bracketed sub-batch runs alone: the other lane starts after it
       CUDA_OK(cudaEventRecord(ev_timed_, stream_));
-      for (auto &O : lane_) if (&O != &L) CUDA_OK(cudaStreamWaitEvent(O.st, ev_timed_, 0));
+      for (int i = 0; i < kDirectLanes; ++i) if (&lane_[i] != &L) CUDA_OK(cudaStreamWaitEvent(lane_[i].st, ev_timed_, 0));
       CUDA_OK(cudaStreamSynchronize(stream_));
       if (prof) {
         std::map<std::string, std::pair<double, int>> acc;
@@ -1157,7 +1191,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       timed = false;
     }
   }
-  for (auto &L : lane_) { CUDA_OK(cudaEventRecord(L.done, L.st)); CUDA_OK(cudaStreamWaitEvent(stream_, L.done, 0)); }
+  for (int i = 0; i < kDirectLanes; ++i) { CUDA_OK(cudaEventRecord(lane_[i].done, lane_[i].st)); CUDA_OK(cudaStreamWaitEvent(stream_, lane_[i].done, 0)); }
   // verification: true residual of every cell (the lifted rhs b is still in d_vec_[2]); read back once per build
   {
     const size_t cap = (size_t)store_groups_ * kLanes;

@@ -116,18 +116,18 @@ int main(int argc, char **argv) {
           band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, ybuf, ldy);                                                  \
     });                                                                                                                \
   }
-  for (int nq : {4, 6, 3}) {
-    if (nq <= 4) OLD(64, 64, nq, 192)
-    NEW(64, 64, 16, 4, 3, nq, 192)
-    NEW(64, 64, 16, 3, 4, nq, 192)
-    NEW(64, 64, 16, 3, 3, nq, 192)
-    NEW(64, 64, 32, 3, 2, nq, 192)
+  for (int nq : {3, 6}) {
     NEW(64, 64, 8, 4, 4, nq, 192)
-    NEW(128, 64, 16, 3, 2, nq, 192)
-    NEW(128, 64, 16, 4, 1, nq, 192)
-    NEW(64, 128, 16, 3, 2, nq, 192)
-    NEW(128, 128, 16, 3, 1, nq, 192)
-    NEW(128, 128, 8, 4, 1, nq, 192)
+    NEW(64, 64, 8, 3, 4, nq, 192)
+    NEW(64, 64, 8, 5, 4, nq, 192)
+    NEW(64, 64, 8, 6, 4, nq, 192)
+    NEW(64, 64, 4, 6, 4, nq, 192)
+    NEW(64, 64, 4, 8, 4, nq, 192)
+    NEW(64, 64, 8, 4, 5, nq, 192)
+    NEW(64, 64, 16, 2, 4, nq, 192)
+    NEW(128, 64, 8, 4, 2, nq, 192)
+    NEW(128, 32, 8, 4, 4, nq, 192)
+    NEW(64, 32, 8, 4, 8, nq, 192)
   }
   // within-chunk window update: 3 panels applied to the rest of the block column (cols 96..192, all rows below)
   std::printf("done\n");

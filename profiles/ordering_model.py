@@ -160,3 +160,32 @@ if __name__ == "__main__":
             for axes in ([2, 1, 0],):
                 b = nd(dofs, n, box, axes, min_cells, sep_split)
                 print(f"nd min_cells={min_cells} sep_split={sep_split}", cost(b, dofs, n))
+
+
+def deferral(dofs, n, keep):
+    """layers/planes with u-type DoFs deferred to the next block so that block sizes are multiples of 32.
+    keep(size) -> number of DoFs the block keeps."""
+    blocks = layers_planes(dofs, n)
+    out = []
+    carry = []
+    for b in blocks:
+        cur = carry + b
+        cur = order_sigma_first(cur, dofs)
+        k = keep(len(cur))
+        if b is blocks[-1]:
+            k = len(cur)
+        # defer the last u-type DoFs
+        n_u = sum(dofs[i][1] for i in cur)
+        d = min(len(cur) - k, n_u)
+        carry = cur[len(cur) - d:] if d > 0 else []
+        out.append(cur[:len(cur) - d] if d > 0 else cur)
+    return out
+
+
+if __name__ == "__main__":
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    dofs = dofs_ned_rt(n)
+    print("current (defer if excess <= 8):", cost(deferral(dofs, n, lambda s: s - s % 32 if 0 < s % 32 <= 8 else s), dofs, n))
+    print("defer down to multiple of 32 always:", cost(deferral(dofs, n, lambda s: s - s % 32), dofs, n))
+    print("defer if excess <= 16:", cost(deferral(dofs, n, lambda s: s - s % 32 if 0 < s % 32 <= 16 else s), dofs, n))
+    print("defer if excess <= 20:", cost(deferral(dofs, n, lambda s: s - s % 32 if 0 < s % 32 <= 20 else s), dofs, n))
