@@ -292,17 +292,24 @@ def main():
                         "bytes_per_launch": bytes_per_launch, "ms_per_launch": spmm_ms,
                         "launches_per_step": int(launches)}
         else:
-            # dominant kernel k_direct_update (FP64 tensor-core trailing update of the block LDL^T):
+            # dominant kernel k_direct_update_s (FP64 tensor-core trailing update of the block LDL^T):
             # algorithmic flops = 2 * 32 * (entries of the lower-triangular trailing region) per launch, summed
             # over the launches that were bracketed by CUDA events (first sub-batch of the step).
             peak, peak_src = fp64_peak(dev)
             ms_upd = st["direct_ms_update"]
             achieved = st["direct_flops_timed"] / (ms_upd * 1e-3) / 1e12 if ms_upd > 0 else 0.0
-            n_timed = max(1, st["direct_update_launches"] * st["direct_flops_timed"] / max(st["direct_flops"], 1.0))
-            roofline = {"bound": "tensor", "kernel": "k_direct_update", "achieved": achieved, "peak": peak,
-                        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            # DRAM traffic per launch of that kernel from the committed ncu --set full capture (profiles/)
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r01_update_s_ncu.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj["mean_dram_bytes_per_launch"], "profiles/r01_update_s_ncu.json: " + tj["capture"]
+            roofline = {"bound": "tensor", "kernel": "k_direct_update_s", "achieved": achieved, "peak": peak,
+                        "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                        "peak_source": peak_src,
                         "flops_per_step": st["direct_flops"], "flops_timed": st["direct_flops_timed"],
-                        "ms_timed": ms_upd, "launches_timed": int(round(n_timed)),
+                        "ms_timed": ms_upd, "launches_timed": int(st["direct_timed_launches"]),
                         "launches_per_step": int(st["direct_update_launches"]),
                         "step_fp64_tflops": st["direct_flops"] / (ms_step * 1e-3) / 1e12}
         line = {

@@ -91,12 +91,12 @@ typedef struct msfec_stats {
   double krylov_ms_spmm;         /* device time inside the SpMM kernel               */
   int64_t krylov_spmm_launches;
   /* direct path ("use direct solver basis = true") */
-  int64_t direct_update_launches;
-  double direct_flops;           /* FP64 flops of all trailing updates of the build (lower triangle) */
-  double direct_flops_timed;     /* flops of the update launches that were bracketed by events       */
-  double direct_ms_update;       /* summed device time of those launches                             */
+  int64_t direct_update_launches;/* k_direct_update_s launches of the build (one per chunk of 32-column panels)     */
+  double direct_flops;           /* FP64 tensor-core flops of the build: trailing updates (lower triangle) + solves */
+  double direct_flops_timed;     /* flops of the k_direct_update_s launches that were bracketed by events           */
+  double direct_ms_update;       /* summed device time of those launches                                            */
   int32_t solver;                /* 0 = batched MINRES, 1 = batched block LDL^T                       */
-  int32_t reserved2;
+  int32_t direct_timed_launches; /* number of event-bracketed k_direct_update_s launches                             */
 } msfec_stats;
 
 typedef struct msfec_ctx msfec_ctx;

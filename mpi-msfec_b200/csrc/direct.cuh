@@ -1,24 +1,29 @@
-// Batched direct solver kernels: block-tridiagonal LDL^T without pivoting (see DirectPlan in
-// topology.h), replacing NedRTBasis::solve_direct (reference ned_rt_basis.cc:579-634, UMFPACK
-// re-factorised for each of the k right-hand sides) for all cells and all k rhs at once.
+// Batched direct solver kernels: block-sparse LDL^T without pivoting (see DirectPlan in topology.h),
+// replacing NedRTBasis::solve_direct (reference ned_rt_basis.cc:579-634, UMFPACK re-factorised for
+// each of the k right-hand sides) for all cells and all k rhs at once.
 //
-// Per cell the "band" holds, for every z-slab s, a column-major panel of ld_s rows
-// [slab s | slab s+1 | 32 rhs rows] x bs_s columns.  Right-looking blocked factorisation with
-// panel width 32:
-//   k_direct_panel   factor the 32x32 diagonal block (one warp, shared memory), then
-//                    row-parallel triangular solve of everything below it (incl. the rhs rows:
-//                    forward substitution is fused into the factorisation)
-//   k_direct_update  trailing update C -= L_r D L_c^T on FP64 tensor cores
-//                    (mma.sync.m8n8k4.f64, 64x64 tiles, 32x32 per warp)
-//   k_direct_backward  L^T x = z for all k rhs, one CTA per cell
-// Included by engine.cu.
+// Per cell the "band" holds, for every block column s, a column-major panel of ld_s rows
+// [block s | reached blocks | 32 rhs rows] x bs_s columns (the rhs ride along as rows, so the forward
+// substitution is part of the factorisation).  A block column is processed in CHUNKS of <= 3 panels of
+// 32 columns (engine.cu: Engine::solve_direct_batch):
+//   k_direct_fill_fused  band := matrix entries / 0 in one coalesced pass
+//   diagonal region of the chunk (96 x 96, small launches per panel):
+//     k_direct_update<128,32>  bring the panel up to date with the earlier panels of the chunk
+//     k_direct_diag            LDL^T of the 32x32 diagonal block (one warp, registers + shuffles) and V = L^-1
+//     k_direct_panel           row-parallel triangular solve of the region rows below it
+//   k_direct_trsm        all rows below the region in one pass: X_p = (A_p - sum X_q L(p,q)^T) V_p^T on
+//                        mma.sync.m8n8k4.f64, writes L = X D^-1 and -X (window scratch)
+//   k_direct_update_s    C -= L D L^T for everything behind the chunk (the dominant kernel): one 64x64 tile
+//                        per CTA, 32x32 per warp, operands through a 4-stage cp.async ring
+//   k_direct_back_gemm / k_direct_back_diag   L^T x = z per block column, last to first
+// Included by engine.cu (and by profiles/microbench_update.cu).
 #pragma once
 
 namespace msfec {
 namespace {
 
 constexpr int kDP = 32;   // panel width (DirectPlan::kPanel)
-constexpr int kMaxWindow = 6;   // panels per delayed update window
+constexpr int kMaxWindow = 6;   // max panels per chunk (slots of the window scratch)
 
 // ---- fill ------------------------------------------------------------------------------
 // per-cell slot entries.  grid (ceil(ne/8), groups), block (32, 8); cell = g*32+lane
@@ -635,96 +640,6 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
   }
   cp_async_wait<0>();
 }
-
-// ---- backward substitution -------------------------------------------------------------
-// L^T x = z.  One CTA (128 threads) per cell; xT[cell][j][NP] is both output and the running
-// solution read by later (lower-numbered) panels.  Per panel of 32 columns:
-//  (1) T = Z - L(below)^T X as a (32 x K) x (K x 24) product on the FP64 tensor cores; the K rows
-//      below the panel are split over the 4 warps, DMMA fragments are read straight from global
-//      memory (each quad of lanes reads one full 32-byte sector), partial sums meet in shared memory;
-//  (2) unit upper-triangular solve with the 32x32 diagonal block, one thread per rhs, column oriented.
-__global__ void __launch_bounds__(128, 6)
-k_direct_backward(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, const double *__restrict__ diagL,
-                  int k, double *xT) {
-  __shared__ double tt[kDP][24 + 1];
-  __shared__ double Ld[kDP][kDP + 1];
-  const int cell = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int fr = lane >> 2, fk = lane & 3;
-  const int NP = D.NP;
-  double *x = xT + (size_t)cell * k * NP;
-  for (int s = D.n_slabs - 1; s >= 0; --s) {
-    const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s], choff = D.chunk_off[s];
-    const int rows_dof = D.front_rows[s], rhs_row = rows_dof;
-    const double *P = band + (size_t)cell * band_stride + D.col_off[s];
-    for (int j0 = bs - kDP; j0 >= 0; j0 -= kDP) {
-      // tt := z (rhs rows of the panel columns), padded rhs columns := 0
-      for (int idx = tid; idx < kDP * 24; idx += 128) {
-        const int c = idx / 24, j = idx % 24;
-        tt[c][j] = j < k ? P[(size_t)(j0 + c) * ld + rhs_row + j] : 0.0;
-      }
-      const double *dl = diagL + ((size_t)cell * NP + so + j0) * kDP;
-      for (int idx = tid; idx < kDP * kDP; idx += 128) {
-        const int i = idx & 31, p = idx >> 5;
-        Ld[i][p] = dl[(size_t)p * kDP + i];
-      }
-      __syncthreads();
-      const int r_lo = j0 + kDP, nsteps = (rows_dof - r_lo) / 4;       // rows_dof, r_lo multiples of 32
-      if (nsteps > 0) {
-        double acc[4][3][2];
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
-        // rows are multiples of 32, so nsteps is a multiple of 8: each of the 4 warps takes pairs of k-steps
-        // and keeps two of them (14 independent sector loads) in flight
-        for (int st = warp * 2; st < nsteps; st += 8) {
-          double af[2][4], bf[2][3];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int i = r_lo + (st + u) * 4 + fk;
-            const int ch = choff + (i >> 5);                  // front row -> padded unknown index
-            const int xi = D.slab_off[D.chunk_blk[ch]] + D.chunk_local[ch] + (i & 31);
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt) af[u][mt] = P[(size_t)(j0 + mt * 8 + fr) * ld + i];   // A[m=c][k=i] = L(i, c)
-#pragma unroll
-            for (int nt = 0; nt < 3; ++nt) {
-              const int j = nt * 8 + fr;
-              bf[u][nt] = j < k ? x[(size_t)j * NP + xi] : 0.0;                                  // B[k=i][n=j] = x_i^(j)
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 2; ++u)
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-              for (int nt = 0; nt < 3; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[u][mt], bf[u][nt]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-          for (int nt = 0; nt < 3; ++nt)
-#pragma unroll
-            for (int h = 0; h < 2; ++h) atomicAdd(&tt[mt * 8 + fr][nt * 8 + fk * 2 + h], -acc[mt][nt][h]);
-      }
-      __syncthreads();
-      if (tid < k) {
-        double t[kDP];
-#pragma unroll
-        for (int c = 0; c < kDP; ++c) t[c] = tt[c][tid];
-#pragma unroll
-        for (int c = kDP - 1; c >= 0; --c) {
-          const double xc = t[c];
-#pragma unroll
-          for (int i = 0; i < c; ++i) t[i] = fma(-Ld[c][i], xc, t[i]);
-        }
-#pragma unroll
-        for (int c = 0; c < kDP; ++c) x[(size_t)tid * NP + so + j0 + c] = t[c];
-      }
-      __syncthreads();
-    }
-  }
-}
-
 
 // ---- backward substitution, block-column version ----------------------------------------
 // L^T x = z, one block column at a time (last to first), two launches per block column:

@@ -732,19 +732,12 @@ class Engine {
             for (int j = 0; j < T_.k_solve; ++j) code[P_.rhs_dest[r] + j] = ((r * 32 + j) << 3) | 4;
         d_dp_code_ = dev_upload(code);
       }
-      if (const char *w = std::getenv("MSFEC_DIRECT_WINDOW")) direct_window_ = std::max(1, std::min(kMaxWindow, std::atoi(w)));
       for (int v : P_.ld) ldy_ = std::max(ldy_, v);
-      CUDA_OK(cudaFuncSetAttribute(k_direct_update<64, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<64, 64>(kMaxWindow)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(kMaxWindow)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update_s<64, 64, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_s_smem<64, 64, 8, 4>()));
       if (const char *b = std::getenv("MSFEC_DIRECT_CHUNK")) direct_chunk_ = std::max(1, std::min(kMaxWindow, std::atoi(b)));
-      if (const char *b = std::getenv("MSFEC_DIRECT_STREAM_UPDATE")) stream_update_ = std::atoi(b) != 0;
-      if (const char *b = std::getenv("MSFEC_DIRECT_TRSM")) use_trsm_ = std::atoi(b) != 0;
-      if (const char *b = std::getenv("MSFEC_DIRECT_BLOCK_BACKWARD")) block_backward_ = std::atoi(b) != 0;
       CUDA_OK(cudaFuncSetAttribute(k_direct_back_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackGemmSmem));
       CUDA_OK(cudaFuncSetAttribute(k_direct_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes(kMaxWindow)));
-      if (!stream_update_) { direct_chunk_ = std::min(direct_chunk_, 4); use_trsm_ = false; }   // resident column operands: K <= 128
-      direct_window_ = std::min(direct_window_, direct_chunk_);
       if (const char *b = std::getenv("MSFEC_DIRECT_LANES")) kDirectLanes = std::max(1, std::min(kMaxDirectLanes, std::atoi(b)));
       {
         // MSFEC_DIRECT_PRIO=1: descending stream priorities (lane 0 highest), so the later lanes fill the gaps
@@ -835,12 +828,8 @@ class Engine {
   // direct solver
   bool use_direct_ = false;
   int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
-  int direct_window_ = 4;                    // panels per delayed trailing update (K = 32 * window)
   int ldy_ = 0;                              // row stride of the window scratch (max front height)
   int direct_chunk_ = 3;                     // panels per chunk (K = 32 * chunk for the update behind a chunk)
-  bool block_backward_ = true;               // backward substitution per block column (k_direct_back_gemm/_diag)
-  bool use_trsm_ = true;                     // rows below a chunk: one DMMA triangular solve (k_direct_trsm)
-  bool stream_update_ = true;                // k_direct_update_s (streamed operands) for window / chunk updates
   int *d_dp_bs_ = nullptr, *d_dp_off_ = nullptr, *d_dp_ld_ = nullptr, *d_dp_front_ = nullptr, *d_dp_choff_ = nullptr,
       *d_dp_chblk_ = nullptr, *d_dp_chloc_ = nullptr, *d_dp_fpos_ = nullptr;
   long long *d_dp_col_ = nullptr;
@@ -862,6 +851,7 @@ class Engine {
   std::vector<cudaEvent_t> ev_upd_;
   double direct_flops_ = 0, direct_ms_update_ = 0, direct_flops_timed_ = 0;
   long direct_update_launches_ = 0;
+  int direct_timed_launches_ = 0;
   void alloc_direct(int nb);
   void free_direct();
   void solve_direct_batch(int groups, int nb, double kscale, msfec_stats &st);
@@ -1064,102 +1054,72 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     mark("fill");
     size_t ev_i = 0;
     std::vector<double> ev_flops;
-    auto launch_update = [&](int s, int jsrc, int nq, int yslot0, int vc_lo, int vc_hi, bool strip, int row_hi = 0) {
+    // C -= L D L^T over the trapezoid columns [vc_lo, vc_hi) x rows [column, row_hi) of block column s, sources =
+    // nq panels from column jsrc (their -L D sits in window-scratch slots 0..nq-1).  strip: one 32-column panel
+    // inside the diagonal region of a chunk (small); otherwise everything behind a chunk (the dominant kernel).
+    auto launch_update = [&](int s, int jsrc, int nq, int vc_lo, int vc_hi, bool strip, int row_hi) {
       const int ld = P_.ld[s];
-      if (row_hi <= 0) row_hi = ld;
       const int c_hi = std::min(vc_hi, P_.front_rows[s]);
       if (c_hi <= vc_lo) return;
       // algorithmic flops: 2 * K * (entries vr >= vc of the target region)
       const double R = row_hi - vc_lo, Cn = c_hi - vc_lo;
       const double flops = 2.0 * kDP * nq * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
       direct_flops_ += flops;
-      const bool tev = timed && ev_i + 2 <= ev_upd_.size();
+      const bool tev = timed && !strip && ev_i + 2 <= ev_upd_.size();
       if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
       if (strip) {
         const int T = (row_hi - vc_lo + 127) / 128;
         k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, yslot0, vc_lo, c_hi, row_hi, d_ybuf_, ldy_);
-      } else if (!stream_update_) {
-        const int Tc = (c_hi - vc_lo + 63) / 64, T = (ld - vc_lo + 63) / 64;
-        int Z = std::max(1, std::min(T, (4 * 148 * 4 + Tc * nc - 1) / (Tc * nc)));   // aim at >= ~16 CTAs per SM
-        k_direct_update<64, 64><<<dim3(Tc, Z, nc), 128, update_smem_bytes<64, 64>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, yslot0, vc_lo, c_hi, ld, d_ybuf_, ldy_);
+            d_band_, stride, D, s, jsrc, nq, 0, vc_lo, c_hi, row_hi, d_ybuf_, ldy_);
       } else {
         k_direct_update_s<64, 64, 8, 4, 4><<<dim3(update_s_tiles<64, 64>(ld, vc_lo, c_hi), nc), 128, update_s_smem<64, 64, 8, 4>(), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, yslot0, vc_lo, c_hi, d_ybuf_, ldy_);
+            d_band_, stride, D, s, jsrc, nq, 0, vc_lo, c_hi, d_ybuf_, ldy_);
+        ++direct_update_launches_;
       }
       if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
-      ++launches_; ++direct_update_launches_;
-      mark(strip ? "update strip" : vc_hi == (1 << 30) ? "update chunk" : "update window");
+      ++launches_;
+      mark(strip ? "update strip" : "update chunk");
     };
     for (int s = 0; s < P_.n_slabs; ++s) {
       const int bs = P_.bs[s], ld = P_.ld[s];
       const int n_panels = bs / kDP;
-      // CHUNKS of at most direct_chunk_ panels: a chunk is applied to everything behind it (rest of the block
-      // column, reached blocks, rhs rows) in one pass once it is complete.  Inside a chunk, equal WINDOWS of at
-      // most direct_window_ panels (5 panels -> 3 + 2): a window is applied to the rest of its chunk only.
+      // equal CHUNKS of at most direct_chunk_ panels (5 panels -> 3 + 2).  Per chunk:
+      //  (1) factor its diagonal region (rows < 32 c1 only: small, latency-bound launches per 32-column panel),
+      //  (2) solve all rows below the region in one pass on the tensor cores (k_direct_trsm),
+      //  (3) apply the chunk to everything behind it: rest of the block column, reached blocks, rhs rows.
       const int n_chunk = (n_panels + direct_chunk_ - 1) / direct_chunk_;
       const int chunk = (n_panels + n_chunk - 1) / n_chunk;
       for (int c0 = 0; c0 < n_panels; c0 += chunk) {
-        const int c1 = std::min(n_panels, c0 + chunk);
-        if (use_trsm_) {
-          // (1) factor the diagonal region of the chunk (rows < 32 c1 only: small launches), (2) solve all rows
-          // below it in one pass on the tensor cores, (3) apply the chunk to everything behind it
-          const int row_hi = c1 * kDP;
-          for (int j = c0; j < c1; ++j) {
-            const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
-            if (j > c0) launch_update(s, c0 * kDP, j - c0, 0, j0, j0 + kDP, true, row_hi);
-            k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_vinv_, d_flag_ + 2);
-            ++launches_;
-            mark("diag");
-            const int nrows = row_hi - (j0 + kDP);
-            if (nrows > 0) {
-              k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, row_hi, j0, pglob, NP, d_diagL_,
-                                                                                 d_dvec_, d_ybuf_, j - c0, ldy_);
-              ++launches_;
-              mark("panel");
-            }
-          }
-          const int np = c1 - c0;
-          k_direct_trsm<<<dim3((ld - row_hi) / kTR, nc), 128, trsm_smem_bytes(np), stream_>>>(
-              d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+        const int c1 = std::min(n_panels, c0 + chunk), np = c1 - c0;
+        const int row_hi = c1 * kDP;
+        for (int j = c0; j < c1; ++j) {
+          const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
+          if (j > c0) launch_update(s, c0 * kDP, j - c0, j0, j0 + kDP, true, row_hi);
+          k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_vinv_, d_flag_ + 2);
           ++launches_;
-          mark("trsm");
-          direct_flops_ += (double)(ld - row_hi) * (np * kDP) * ((np + 1) * kDP) * nc;   // 2 * rows * 32^2 * np(np+1)/2
-        } else {
-          const int n_win = (c1 - c0 + direct_window_ - 1) / direct_window_;
-          const int win = (c1 - c0 + n_win - 1) / n_win;
-          for (int p0 = c0; p0 < c1; p0 += win) {
-            const int pe = std::min(c1, p0 + win);
-            for (int j = p0; j < pe; ++j) {
-              const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
-              // bring panel j up to date with the earlier panels of this window, then factor it
-              if (j > p0) launch_update(s, p0 * kDP, j - p0, p0 - c0, j0, j0 + kDP, true);
-              const int nrows = ld - (j0 + kDP);
-              k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, nullptr, d_flag_ + 2);
-              k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, ld, j0, pglob, NP, d_diagL_, d_dvec_,
-                                                                                 d_ybuf_, j - c0, ldy_);
-              launches_ += 2;
-              mark("diag+panel");
-            }
-            // apply the window to the rest of its chunk
-            if (pe < c1) launch_update(s, p0 * kDP, pe - p0, p0 - c0, pe * kDP, c1 * kDP, false);
+          mark("diag");
+          const int nrows = row_hi - (j0 + kDP);
+          if (nrows > 0) {
+            k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, row_hi, j0, pglob, NP, d_diagL_,
+                                                                               d_dvec_, d_ybuf_, j - c0, ldy_);
+            ++launches_;
+            mark("panel");
           }
         }
-        // apply the whole chunk to everything behind it
-        launch_update(s, c0 * kDP, c1 - c0, 0, c1 * kDP, 1 << 30, false);
+        k_direct_trsm<<<dim3((ld - row_hi) / kTR, nc), 128, trsm_smem_bytes(np), stream_>>>(
+            d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+        ++launches_;
+        mark("trsm");
+        direct_flops_ += (double)(ld - row_hi) * (np * kDP) * ((np + 1) * kDP) * nc;   // 2 * rows * 32^2 * np(np+1)/2
+        launch_update(s, c0 * kDP, np, row_hi, 1 << 30, false, ld);
       }
     }
-    if (block_backward_ && use_trsm_) {
-      for (int sb = P_.n_slabs - 1; sb >= 0; --sb) {
-        const bool below = P_.front_rows[sb] > P_.bs[sb];
-        if (below) k_direct_back_gemm<<<dim3(P_.bs[sb] / kDP, nc), 128, kBackGemmSmem, stream_>>>(d_band_, stride, D, sb, k, d_xT_);
-        k_direct_back_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, D, sb, k, nc, d_vinv_, below ? 0 : 1, d_xT_);
-        launches_ += below ? 2 : 1;
-      }
-    } else {
-      k_direct_backward<<<nc, 128, 0, stream_>>>(d_band_, stride, D, d_diagL_, k, d_xT_);
-      ++launches_;
+    // backward substitution, block columns last to first
+    for (int sb = P_.n_slabs - 1; sb >= 0; --sb) {
+      const bool below = P_.front_rows[sb] > P_.bs[sb];
+      if (below) k_direct_back_gemm<<<dim3(P_.bs[sb] / kDP, nc), 128, kBackGemmSmem, stream_>>>(d_band_, stride, D, sb, k, d_xT_);
+      k_direct_back_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, D, sb, k, nc, d_vinv_, below ? 0 : 1, d_xT_);
+      launches_ += below ? 2 : 1;
     }
     mark("backward");
     k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
@@ -1186,7 +1146,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       for (size_t i = 0; i + 1 < ev_i + 1 && i / 2 < ev_flops.size(); i += 2) {
         float ms = 0;
         CUDA_OK(cudaEventElapsedTime(&ms, ev_upd_[i], ev_upd_[i + 1]));
-        direct_ms_update_ += ms; direct_flops_timed_ += ev_flops[i / 2];
+        direct_ms_update_ += ms; direct_flops_timed_ += ev_flops[i / 2]; ++direct_timed_launches_;
       }
       timed = false;
     }
@@ -1210,7 +1170,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   msfec_stats st{};
   st.n_cells = n_cells; st.k = T_.k_gram; st.n_fine_dofs = T_.NF; st.n_fine_dofs_interior = T_.NI;
   launches_ = 0; spmm_samples_ = 0; cell_iters_ = 0;
-  direct_flops_ = direct_ms_update_ = direct_flops_timed_ = 0; direct_update_launches_ = 0;
+  direct_flops_ = direct_ms_update_ = direct_flops_timed_ = 0; direct_update_launches_ = 0; direct_timed_launches_ = 0;
   have_weights_ = false;
   alloc_store(n_cells);
   const int kg = T_.k_gram;
@@ -1335,6 +1295,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   st.krylov_ms_spmm = spmm_samples_ ? ms_spmm / spmm_samples_ : 0.0;   // mean duration of one SpMM launch
   st.direct_flops = direct_flops_; st.direct_flops_timed = direct_flops_timed_; st.direct_ms_update = direct_ms_update_;
   st.direct_update_launches = direct_update_launches_; st.solver = use_direct_ ? 1 : 0;
+  st.direct_timed_launches = direct_timed_launches_;
   if (stats) *stats = st;
   return st.not_converged ? MSFEC_ENOTCONVERGED : MSFEC_OK;
 }

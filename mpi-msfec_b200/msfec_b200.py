@@ -50,7 +50,7 @@ class Stats(C.Structure):
         ("ms_total", C.c_double), ("krylov_matrix_bytes", C.c_double), ("krylov_ms_spmm", C.c_double),
         ("krylov_spmm_launches", C.c_int64),
         ("direct_update_launches", C.c_int64), ("direct_flops", C.c_double), ("direct_flops_timed", C.c_double),
-        ("direct_ms_update", C.c_double), ("solver", C.c_int32), ("reserved2", C.c_int32),
+        ("direct_ms_update", C.c_double), ("solver", C.c_int32), ("direct_timed_launches", C.c_int32),
     ]
 
     def as_dict(self):
