@@ -105,7 +105,7 @@ int main(int argc, char **argv) {
     run("resident<" #TM "," #TN ">", nq, vc_lo, [&] {                                                                  \
       const int Tc = (544 - vc_lo + TN - 1) / TN, T = (576 - vc_lo + TM - 1) / TM;                                     \
       int Z = std::max(1, std::min(T, (4 * 148 * 4 + Tc * cells - 1) / (Tc * cells)));                                 \
-      k_direct_update<TM, TN><<<dim3(Tc, Z, cells), (TM / 32) * (TN / 32) * 32, update_smem_bytes<TM, TN>(nq)>>>(band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, ybuf, ldy); \
+      k_direct_update<TM, TN><<<dim3(Tc, Z, cells), (TM / 32) * (TN / 32) * 32, update_smem_bytes<TM, TN>(nq)>>>(band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, 576, ybuf, ldy); \
     });                                                                                                                \
   }
 #define NEW(TM, TN, KC, ST, MB, nq, vc_lo)                                                                             \
@@ -116,24 +116,14 @@ int main(int argc, char **argv) {
           band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, ybuf, ldy);                                                  \
     });                                                                                                                \
   }
-#define TMA(KC, ST, MB, nq, vc_lo)                                                                                     \
-  {                                                                                                                    \
-    CUDA_OK(cudaFuncSetAttribute(k_direct_update_t<KC, ST, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_t_smem<KC, ST>())); \
-    run("tma<" #KC "," #ST "," #MB ">", nq, vc_lo, [&] {                                                              \
-      k_direct_update_t<KC, ST, MB><<<dim3(update_s_tiles<64, 64>(576, vc_lo, 544), cells), 128, update_t_smem<KC, ST>()>>>( \
-          band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, ybuf, ldy);                                                  \
-    });                                                                                                                \
-  }
-  for (int nq : {3, 6}) {
+  for (int nq : {3, 4, 6}) {
+    if (nq <= 4) OLD(64, 64, nq, 192)
     NEW(64, 64, 8, 4, 4, nq, 192)
-    TMA(8, 4, 4, nq, 192)
-    TMA(8, 5, 4, nq, 192)
-    TMA(8, 6, 4, nq, 192)
-    TMA(16, 3, 4, nq, 192)
-    TMA(16, 4, 3, nq, 192)
-    TMA(4, 8, 4, nq, 192)
+    NEW(64, 64, 16, 2, 4, nq, 192)
+    NEW(64, 64, 16, 4, 3, nq, 192)
+    NEW(128, 64, 8, 4, 2, nq, 192)
+    NEW(128, 32, 8, 4, 4, nq, 192)
   }
-  // within-chunk window update: 3 panels applied to the rest of the block column (cols 96..192, all rows below)
   std::printf("done\n");
   return 0;
 }
