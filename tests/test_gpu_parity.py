@@ -120,6 +120,38 @@ def test_structure_properties_at_scale(msfec, direct):
     assert worst < TOL
 
 
+def test_full_size_c5_properties(msfec):
+    """BASELINE.json configs[4] at full size (32 768 random-field cells x 3 local refinements, direct path):
+    size-independent properties over ALL cells, batch independence (a cell solved inside the full job equals the
+    same cell solved in a job of its own and in a ragged 33-cell job) and three cells against the oracle."""
+    cells = mo.morton_cells(5)
+    assert len(cells) == 32768
+    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017, use_direct_solver_basis=1)
+    ids = np.arange(32768)
+    bb = msfec.BasisBuilder(p, device=0).run(cells, cell_ids=ids)
+    M = bb.get_global_element_matrix().copy(); r = bb.get_global_element_rhs().copy()
+    st = dict(bb.stats)
+    assert st["not_converged"] == 0 and st["residual_max"] < 1e-11          # true residual of every cell
+    s = np.abs(M).max(axis=(1, 2))
+    assert np.isfinite(M).all() and np.isfinite(r).all() and (s > 0).all()
+    assert (np.abs(M[:, :12, :12] - M[:, :12, :12].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    assert (np.abs(M[:, 12:, 12:] - M[:, 12:, 12:].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    assert (np.abs(M[:, :12, 12:] + M[:, 12:, :12].transpose(0, 2, 1)).max(axis=(1, 2)) < 1e-9 * s).all()
+    # the (0,0) block is a Gram matrix of the A^-1 inner product: positive diagonal
+    assert (np.einsum("cii->ci", M[:, :12, :12]) > 0).all()
+    # batch independence: ids select the random field, so sub-jobs reproduce the same cells
+    for sel in (np.array([20000]), np.arange(4090, 4123)):
+        bb2 = msfec.BasisBuilder(p, device=0).run(cells[sel], cell_ids=ids[sel])
+        M2 = bb2.get_global_element_matrix()
+        assert np.abs(M2 - M[sel]).max() <= 1e-11 * s[sel].max()
+        bb2.close()
+    prob = oracle_problem("NED_RT", 3, random_seed=20261017)
+    for c in (0, 12345, 32767):
+        Mo, ro, *_ = mo.build_basis(prob, cells[c], c)
+        assert rel_err(M[c], Mo) < TOL and np.abs(r[c] - ro).max() <= TOL * max(np.abs(ro).max(), 1e-300)
+    bb.close()
+
+
 def test_error_paths(msfec):
     p = lib_problem(msfec, "Q", 2)
     bb = msfec.BasisBuilder(p, device=0)
