@@ -474,9 +474,11 @@ __global__ void k_finalize_basis(BasisDims D, const double *__restrict__ x, cons
   }
 }
 
-// Y = Full * Z.  grid (ceil(NF/4), groups), block (32, 4)
-__global__ void k_apply_full(OpDev A, int NF, int kg, int n_slots, double kscale, const double *__restrict__ vals,
-                             const double *__restrict__ Z, int gz0, double *__restrict__ Y) {
+// Y = Full * Z.  grid (ceil(NF/4), groups), block (32, 4).  Z is block sparse: rows of block 0 (d < N0) carry only
+// the k0 sigma-type coarse functions, rows of block 1 only the u-type ones (finalize_basis), so an entry with column
+// c touches only the basis columns of c's block (Ned_RT: 12 or 6 of 18) -- half the loads and FMAs.
+__global__ void k_apply_full(OpDev A, int NF, int N0, int k0, int kg, int n_slots, double kscale,
+                             const double *__restrict__ vals, const double *__restrict__ Z, int gz0, double *__restrict__ Y) {
   const int lane = threadIdx.x, g = blockIdx.y;
   const int row = blockIdx.x * blockDim.y + threadIdx.y;
   if (row >= NF) return;
@@ -485,20 +487,19 @@ __global__ void k_apply_full(OpDev A, int NF, int kg, int n_slots, double kscale
   double acc[kMaxK];
 #pragma unroll
   for (int j = 0; j < kMaxK; ++j) acc[j] = 0.0;
+  auto axpy = [&](double a, int col) {
+    const double *z = zg + (size_t)col * kg * kLanes;
+    const int jlo = col < N0 ? 0 : k0, jhi = col < N0 ? k0 : kg;
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) if (j >= jlo && j < jhi) acc[j] = fma(a, z[j * kLanes], acc[j]);
+  };
   for (int e = A.cptr[row]; e < A.cptr[row + 1]; ++e) {
     const int ref = A.cref[e];
     double a = v[(size_t)(ref >> 1) * kLanes];
     if (ref & 1) a = -a;
-    const double *z = zg + (size_t)A.ccol[e] * kg * kLanes;
-#pragma unroll
-    for (int j = 0; j < kMaxK; ++j) if (j < kg) acc[j] = fma(a, z[j * kLanes], acc[j]);
+    axpy(a, A.ccol[e]);
   }
-  for (int e = A.sptr[row]; e < A.sptr[row + 1]; ++e) {
-    const double a = A.sval[e] * kscale;
-    const double *z = zg + (size_t)A.scol[e] * kg * kLanes;
-#pragma unroll
-    for (int j = 0; j < kMaxK; ++j) if (j < kg) acc[j] = fma(a, z[j * kLanes], acc[j]);
-  }
+  for (int e = A.sptr[row]; e < A.sptr[row + 1]; ++e) axpy(A.sval[e] * kscale, A.scol[e]);
 #pragma unroll
   for (int j = 0; j < kMaxK; ++j) if (j < kg) Y[(((size_t)g * NF + row) * kg + j) * kLanes + lane] = acc[j];
 }
@@ -1234,7 +1235,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
                 T_.two_blocks ? T_.blk[1].n_total : 0, T_.blk[0].n_total - T_.blk[0].n_int, T_.NI, T_.NB, T_.NF,
                 T_.k_solve, kg, T_.k0, T_.pairing == MSFEC_RT_DQ ? 1 : 0};
     k_finalize_basis<<<dim3((T_.NF + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(D, d_vec_[7], d_G_, d_Z_, gz0);
-    k_apply_full<<<dim3((T_.NF + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(full_.dev, T_.NF, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
+    k_apply_full<<<dim3((T_.NF + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(full_.dev, T_.NF, T_.blk[0].n_total, T_.k0, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
     const int rhs_off = T_.rhs_block ? T_.blk[0].n_total : 0;
     {
       const int n_slices = std::max(1, std::min(16, (2 * 148 + groups - 1) / groups));
