@@ -641,12 +641,11 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
   cp_async_wait<0>();
 }
 
-// ---- backward substitution, block-column version ----------------------------------------
-// L^T x = z, one block column at a time (last to first), two launches per block column:
-//  k_direct_back_gemm   T = z - L(rows below the block, block columns)^T x(front)  for all 32-column panels of
-//                       the block column in parallel: grid (bs/32, cells).  The K = front rows below the block
-//                       stream through a 4-stage cp.async ring of 32-row slices, so the band is read at HBM
-//                       speed with long contiguous runs (the per-cell persistent kernel above is latency bound).
+// ---- backward substitution, chunk by chunk ------------------------------------------------
+// L^T x = z, chunks of <= 3 panels in reverse elimination order, two launches per chunk:
+//  k_direct_back_gemm   T = z - L(rows below the chunk's diagonal region, chunk columns)^T x  for all panels of the
+//                       chunk in parallel: grid (panels, cells).  The rows stream through a 4-stage cp.async ring
+//                       of 32-row slices, so the band is read at HBM speed with long contiguous runs.
 //  k_direct_back_diag   x = L_dd^-T T inside the diagonal region: one warp per cell, panels last to first,
 //                       x_p = V_p^T (T_p - sum_{q>p} L(q,p)^T x_q), all products on mma.sync.m8n8k4.f64.
 // xT[cell][j][NP] holds T between the two launches and x afterwards.
@@ -654,15 +653,16 @@ constexpr int kBLd = kDP + 4, kBStages = 4;
 constexpr size_t kBackGemmSmem = (size_t)kBStages * (kDP + 24) * kBLd * sizeof(double);
 
 __global__ void __launch_bounds__(128)
-k_direct_back_gemm(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int k, double *xT) {
+k_direct_back_gemm(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int panel0, int i_lo, int k,
+                   double *xT) {
   extern __shared__ __align__(16) double bg_smem[];        // [stage][32 cols + 24 rhs][kBLd]
-  const int cell = blockIdx.y, j0 = blockIdx.x * kDP, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cell = blockIdx.y, j0 = (panel0 + blockIdx.x) * kDP, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;
-  const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s], choff = D.chunk_off[s], rows_dof = D.front_rows[s];
+  const int ld = D.ld[s], so = D.slab_off[s], choff = D.chunk_off[s], rows_dof = D.front_rows[s];
   const int NP = D.NP;
   const double *P = band + (size_t)cell * band_stride + D.col_off[s];
   double *x = xT + (size_t)cell * k * NP;
-  const int nst = (rows_dof - bs) / kDP;                   // 32-row slices below the block
+  const int nst = (rows_dof - i_lo) / kDP;                 // 32-row slices below the chunk's diagonal region
   // rhs rows >= k of every stage stay zero
   for (int i = tid; i < kBStages * 24 * kBLd; i += 128) {
     const int st = i / (24 * kBLd), r = i % (24 * kBLd);
@@ -670,7 +670,7 @@ k_direct_back_gemm(const double *__restrict__ band, size_t band_stride, DirectPl
   }
   auto load_stage = [&](int t) {
     double *dst = bg_smem + (size_t)(t % kBStages) * (kDP + 24) * kBLd;
-    const int i0 = bs + t * kDP;                           // first front row of the slice
+    const int i0 = i_lo + t * kDP;                         // first front row of the slice
     const int ch = choff + (i0 >> 5);
     const int xi = D.slab_off[D.chunk_blk[ch]] + D.chunk_local[ch];   // padded unknown index of that row
 #pragma unroll
@@ -717,20 +717,19 @@ k_direct_back_gemm(const double *__restrict__ band, size_t band_stride, DirectPl
     }
 }
 
-// grid (ceil(cells/4)), block 128 (warp per cell).  from_z: the block column has no rows below it (T = z).
+// grid (ceil(cells/4)), block 128 (warp per cell); panels [p_lo, p_hi) of block column s.  from_z: no rows below (T = z).
 __global__ void __launch_bounds__(128)
-k_direct_back_diag(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int k, int n_cells,
-                   const double *__restrict__ vinv, int from_z, double *xT) {
+k_direct_back_diag(const double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int p_lo, int p_hi, int k,
+                   int n_cells, const double *__restrict__ vinv, int from_z, double *xT) {
   __shared__ double ts[4][kDP][24 + 1];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cell = blockIdx.x * 4 + w;
   if (cell >= n_cells) return;
   const int fr = lane >> 2, fk = lane & 3;
-  const int bs = D.bs[s], ld = D.ld[s], so = D.slab_off[s], rows_dof = D.front_rows[s], NP = D.NP;
+  const int ld = D.ld[s], so = D.slab_off[s], rows_dof = D.front_rows[s], NP = D.NP;
   const double *P = band + (size_t)cell * band_stride + D.col_off[s];
   double *x = xT + (size_t)cell * k * NP;
-  const int np = bs / kDP;
-  for (int p = np - 1; p >= 0; --p) {
+  for (int p = p_hi - 1; p >= p_lo; --p) {
     const int j0 = p * kDP;
     double acc[4][3][2];
     // t := T_p (m = column c, n = rhs j)
@@ -744,7 +743,7 @@ k_direct_back_diag(const double *__restrict__ band, size_t band_stride, DirectPl
           acc[mt][nt][h] = j < k ? (from_z ? P[(size_t)(j0 + c) * ld + rows_dof + j] : x[(size_t)j * NP + so + j0 + c]) : 0.0;
         }
     // t -= L(q,p)^T x_q for the panels q > p of this block column
-    for (int q = p + 1; q < np; ++q) {
+    for (int q = p + 1; q < p_hi; ++q) {
       const double *Lq = P + (size_t)(j0 + fr) * ld + q * kDP + fk;
       const double *xq = x + (size_t)fr * NP + so + q * kDP + fk;
 #pragma unroll

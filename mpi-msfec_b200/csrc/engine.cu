@@ -838,11 +838,11 @@ class Engine {
       *d_dp_rhs_ = nullptr, *d_dp_code_ = nullptr;
   bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
-  // sub-batches are processed round-robin on kDirectLanes streams with private band storage, so the latency-bound
-  // phases of one sub-batch (diagonal blocks, panel solves, backward substitution, band memset) overlap with the
-  // compute-bound trailing updates of the other
+  // sub-batches can be processed round-robin on several streams ("lanes") with private band storage; measured on
+  // B200 this gains nothing (every large kernel fills the GPU and kernels of different streams effectively run
+  // one after the other), and one lane gives small jobs twice the cells per launch, so the default is 1
   static constexpr int kMaxDirectLanes = 4;
-  int kDirectLanes = 2;                      // MSFEC_DIRECT_LANES (1..4)
+  int kDirectLanes = 1;                      // MSFEC_DIRECT_LANES (1..4): more lanes measured no faster (kernels fill the GPU)
   struct DirectLane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
@@ -1115,12 +1115,18 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
         launch_update(s, c0 * kDP, np, row_hi, 1 << 30, false, ld);
       }
     }
-    // backward substitution, block columns last to first
+    // backward substitution: chunks in reverse elimination order
     for (int sb = P_.n_slabs - 1; sb >= 0; --sb) {
-      const bool below = P_.front_rows[sb] > P_.bs[sb];
-      if (below) k_direct_back_gemm<<<dim3(P_.bs[sb] / kDP, nc), 128, kBackGemmSmem, stream_>>>(d_band_, stride, D, sb, k, d_xT_);
-      k_direct_back_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, D, sb, k, nc, d_vinv_, below ? 0 : 1, d_xT_);
-      launches_ += below ? 2 : 1;
+      const int n_panels = P_.bs[sb] / kDP;
+      const int n_chunk = (n_panels + direct_chunk_ - 1) / direct_chunk_;
+      const int chunk = (n_panels + n_chunk - 1) / n_chunk;
+      for (int c0 = (n_chunk - 1) * chunk; c0 >= 0; c0 -= chunk) {
+        const int c1 = std::min(n_panels, c0 + chunk);
+        const bool below = P_.front_rows[sb] > c1 * kDP;
+        if (below) k_direct_back_gemm<<<dim3(c1 - c0, nc), 128, kBackGemmSmem, stream_>>>(d_band_, stride, D, sb, c0, c1 * kDP, k, d_xT_);
+        k_direct_back_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, D, sb, c0, c1, k, nc, d_vinv_, below ? 0 : 1, d_xT_);
+        launches_ += below ? 2 : 1;
+      }
     }
     mark("backward");
     k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
