@@ -986,8 +986,8 @@ void Engine::free_direct() {
 }
 
 void Engine::alloc_direct(int nb) {
-  // cells per sub-batch: bounded by a memory budget for the bands of all lanes (default 24 GB), multiple of 32
-  double budget_gb = 24.0;
+  // cells per sub-batch: bounded by a memory budget for the bands of all lanes (default 48 GB), multiple of 32
+  double budget_gb = 48.0;
   if (const char *e = std::getenv("MSFEC_DIRECT_BAND_GB")) budget_gb = std::atof(e);
   long sub = (long)(budget_gb * 1e9 / kDirectLanes / ((double)P_.band_doubles * 8.0));
   if (const char *e = std::getenv("MSFEC_DIRECT_BATCH")) sub = std::atol(e);
