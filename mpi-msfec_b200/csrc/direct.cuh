@@ -511,28 +511,36 @@ k_direct_update_s(double *__restrict__ band, size_t band_stride, DirectPlanDev D
 // L = X D^-1 in place and -X to the window scratch (slot p) for the chunk update.  Every band entry of these
 // rows is read once and written once (the 32-wide panel kernels moved it ~5 times).
 // grid ((ld - row_lo) / 32, cells), block 128 (warp = 16 columns x 16 rows of the current panel)
-constexpr int kTR = 32, kTLd = kTR + 4, kTBs = kDP + 4;
+constexpr int kTBs = kDP + 4;
+template <int TR>
 constexpr size_t trsm_smem_bytes(int np) {
-  return ((size_t)np * kDP * kTLd + 3 * kDP * kTBs + kDP * kTLd + (size_t)np * kDP) * sizeof(double);
+  return ((size_t)np * kDP * (TR + 4) + 3 * kDP * kTBs + kDP * (TR + 4) + (size_t)np * kDP) * sizeof(double);
 }
 
+// TR rows per CTA (32 or 64): a warp owns 16 columns x TR/2 rows of the current panel.  TR = 64 halves the number
+// of times the 32x32 operand blocks are re-streamed from L2 and doubles the independent MMAs per fragment load;
+// the last CTA of a launch may own only 32 valid rows (row counts are multiples of 32).
+template <int TR>
 __global__ void __launch_bounds__(128)
 k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int jc0, int np, int row_lo,
               int pglob0, int NP, const double *__restrict__ vinv, const double *__restrict__ dvec,
               double *__restrict__ ybuf, int ldy) {
+  constexpr int kTLd = TR + 4, NTL = TR / 16, WR = TR / 2;   // smem row stride, n-tiles and rows per warp
   extern __shared__ __align__(16) double trsm_smem[];
   double *Xs = trsm_smem;                                  // [32 np][kTLd]   A, then X
   double *Bs = Xs + (size_t)np * kDP * kTLd;               // [3][32][kTBs]   operand ring, [k][n]
   double *Ts = Bs + 3 * kDP * kTBs;                        // [32][kTLd]      T_p as MMA operand
   double *dinv = Ts + kDP * kTLd;                          // [32 np]
   const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int r0 = row_lo + blockIdx.x * kTR;
+  const int r0 = row_lo + blockIdx.x * TR;
   double *P = band + (size_t)cell * band_stride + col_off;
   const int W = np * kDP;
-  // stage the A tile: W columns x 32 rows = 16 chunks of 16 bytes per column
-  for (int c = tid; c < W * (kTR / 2); c += 128) {
-    const int k = c / (kTR / 2), i = (c % (kTR / 2)) * 2;
-    cp_async16(Xs + k * kTLd + i, P + (size_t)(jc0 + k) * ld + r0 + i);
+  // stage the A tile: W columns x TR rows = TR/2 chunks of 16 bytes per column
+  for (int c = tid; c < W * (TR / 2); c += 128) {
+    const int k = c / (TR / 2), i = (c % (TR / 2)) * 2;
+    double *d = Xs + k * kTLd + i;
+    if (r0 + i < ld) cp_async16(d, P + (size_t)(jc0 + k) * ld + r0 + i);
+    else { d[0] = 0.0; d[1] = 0.0; }
   }
   cp_async_commit();
   for (int c = tid; c < W; c += 128) dinv[c] = 1.0 / dvec[(size_t)cell * NP + pglob0 + c];
@@ -560,7 +568,8 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
   }
   const int wm = warp >> 1, wn = warp & 1;                 // wm: column half (MMA m), wn: row half (MMA n)
   const int fr = lane >> 2, fk = lane & 3;
-  double acc[2][2][2];
+  const bool rows_valid = r0 + wn * WR < ld;               // warp-uniform (valid rows come in multiples of 32)
+  double acc[2][NTL][2];
   int p = 0, q = 0;
   for (int b = 0; b < nblk; ++b) {
     cp_async_wait<1>();
@@ -569,56 +578,60 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
     cp_async_commit();
     const double *Bb = Bs + (size_t)(b % 3) * kDP * kTBs + wm * 16 + fr;
     if (q == 0 && p > 0) {
-      // acc := A_p (own 16 columns x 16 rows)
+      // acc := A_p (own 16 columns x WR rows)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const double2 v = *reinterpret_cast<const double2 *>(Xs + (size_t)(p * kDP + wm * 16 + mt * 8 + fr) * kTLd + wn * 16 + nt * 8 + fk * 2);
+        for (int nt = 0; nt < NTL; ++nt) {
+          const double2 v = *reinterpret_cast<const double2 *>(Xs + (size_t)(p * kDP + wm * 16 + mt * 8 + fr) * kTLd + wn * WR + nt * 8 + fk * 2);
           acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
         }
     }
     if (q < p) {
       // acc -= L(p,q) X_q^T   (m = column of panel p, k = column of panel q, n = row)
-      const double *Xq = Xs + (size_t)(q * kDP) * kTLd + wn * 16 + fr;
+      const double *Xq = Xs + (size_t)(q * kDP) * kTLd + wn * WR + fr;
 #pragma unroll
       for (int ks = 0; ks < kDP / 4; ++ks) {
         const int kk = ks * 4 + fk;
-        double af[2], bf[2];
+        double af[2], bf[NTL];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) { af[t] = -Bb[kk * kTBs + t * 8]; bf[t] = Xq[kk * kTLd + t * 8]; }
+        for (int t = 0; t < 2; ++t) af[t] = -Bb[kk * kTBs + t * 8];
+#pragma unroll
+        for (int t = 0; t < NTL; ++t) bf[t] = Xq[kk * kTLd + t * 8];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+          for (int nt = 0; nt < NTL; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
       if (q == p - 1) {
         // T_p complete: publish it as an MMA operand for the V_p product (visible after the next barrier)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
-            *reinterpret_cast<double2 *>(Ts + (size_t)(wm * 16 + mt * 8 + fr) * kTLd + wn * 16 + nt * 8 + fk * 2) =
+          for (int nt = 0; nt < NTL; ++nt)
+            *reinterpret_cast<double2 *>(Ts + (size_t)(wm * 16 + mt * 8 + fr) * kTLd + wn * WR + nt * 8 + fk * 2) =
                 make_double2(acc[mt][nt][0], acc[mt][nt][1]);
       }
     } else {
       // X_p = V_p T_p  (m = column n' of panel p, k = column of T_p, n = row); for p = 0, T_0 = A_0 sits in Xs
-      const double *Tq = (p == 0 ? Xs : Ts) + wn * 16 + fr;
-      double x[2][2][2];
+      const double *Tq = (p == 0 ? Xs : Ts) + wn * WR + fr;
+      double x[2][NTL][2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) x[mt][nt][0] = x[mt][nt][1] = 0.0;
+        for (int nt = 0; nt < NTL; ++nt) x[mt][nt][0] = x[mt][nt][1] = 0.0;
 #pragma unroll
       for (int ks = 0; ks < kDP / 4; ++ks) {
         const int kk = ks * 4 + fk;
-        double af[2], bf[2];
+        double af[2], bf[NTL];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) { af[t] = Bb[kk * kTBs + t * 8]; bf[t] = Tq[kk * kTLd + t * 8]; }
+        for (int t = 0; t < 2; ++t) af[t] = Bb[kk * kTBs + t * 8];
+#pragma unroll
+        for (int t = 0; t < NTL; ++t) bf[t] = Tq[kk * kTLd + t * 8];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 2; ++nt) dmma_m8n8k4(x[mt][nt][0], x[mt][nt][1], af[mt], bf[nt]);
+          for (int nt = 0; nt < NTL; ++nt) dmma_m8n8k4(x[mt][nt][0], x[mt][nt][1], af[mt], bf[nt]);
       }
       if (p == 0) __syncthreads();                         // everyone has read A_0 before it is overwritten by X_0
       double *Y = ybuf + ((size_t)cell * kMaxWindow + p) * kDP * ldy;
@@ -627,12 +640,14 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
         const int col = wm * 16 + mt * 8 + fr;             // column inside panel p
         const double di = dinv[p * kDP + col];
 #pragma unroll
-        for (int nt = 0; nt < 2; ++nt) {
-          const int row = wn * 16 + nt * 8 + fk * 2;
+        for (int nt = 0; nt < NTL; ++nt) {
+          const int row = wn * WR + nt * 8 + fk * 2;
           const double x0 = x[mt][nt][0], x1 = x[mt][nt][1];
           *reinterpret_cast<double2 *>(Xs + (size_t)(p * kDP + col) * kTLd + row) = make_double2(x0, x1);
-          *reinterpret_cast<double2 *>(P + (size_t)(jc0 + p * kDP + col) * ld + r0 + row) = make_double2(x0 * di, x1 * di);
-          *reinterpret_cast<double2 *>(Y + (size_t)col * ldy + r0 + row) = make_double2(-x0, -x1);
+          if (rows_valid) {
+            *reinterpret_cast<double2 *>(P + (size_t)(jc0 + p * kDP + col) * ld + r0 + row) = make_double2(x0 * di, x1 * di);
+            *reinterpret_cast<double2 *>(Y + (size_t)col * ldy + r0 + row) = make_double2(-x0, -x1);
+          }
         }
       }
     }

@@ -85,30 +85,48 @@ __global__ void k_sample_coefficients(CoefParams P, const ExprInstr *__restrict_
   const double px = x0[(g * 3 + 0) * kLanes + lane] + h * (ci + gq[q & 1]);
   const double py = x0[(g * 3 + 1) * kLanes + lane] + h * (cj + gq[(q >> 1) & 1]);
   const double pz = x0[(g * 3 + 2) * kLanes + lane] + h * (ck + gq[q >> 2]);
-  double d[3], s;
+  double *o = coef + ((size_t)(g * P.nC + T) * 56 + q * 7) * kLanes + lane;
   if (P.use_random) {
-    double xi[4];
-    field_normals(P.seed, (unsigned long long)gid[g * kLanes + lane] * (unsigned long long)P.nC + T, xi);
-    d[0] = exp(P.sigma * xi[0]); d[1] = exp(P.sigma * xi[1]); d[2] = exp(P.sigma * xi[2]);
-    s = exp(P.sigma * xi[3]);
+    // piecewise constant per fine cell: the 8 Gauss points share one sample, so one warp evaluates the
+    // normals / exponentials / rotation and the other seven copy the 7 channels from shared memory
+    __shared__ double ch[7][kLanes];
+    if (q == 0) {
+      double xi[4], d[3];
+      field_normals(P.seed, (unsigned long long)gid[g * kLanes + lane] * (unsigned long long)P.nC + T, xi);
+      d[0] = exp(P.sigma * xi[0]); d[1] = exp(P.sigma * xi[1]); d[2] = exp(P.sigma * xi[2]);
+      double s = exp(P.sigma * xi[3]);
+      if (P.tensor_inverse) { d[0] = 1.0 / d[0]; d[1] = 1.0 / d[1]; d[2] = 1.0 / d[2]; }
+      if (P.scalar_inverse) s = 1.0 / s;
+      int c = 0;
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = a; b < 3; ++b)
+          ch[c++][lane] = P.rot[a * 3 + 0] * d[0] * P.rot[b * 3 + 0] + P.rot[a * 3 + 1] * d[1] * P.rot[b * 3 + 1] +
+                          P.rot[a * 3 + 2] * d[2] * P.rot[b * 3 + 2];
+      ch[6][lane] = s;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 7; ++c) o[c * kLanes] = ch[c][lane];
   } else {
+    double d[3], s;
     d[0] = P.a_scale[0] * (1.0 - P.a_alpha[0] * sin(2.0 * M_PI * P.a_freq[0] * px));
     d[1] = P.a_scale[1] * (1.0 - P.a_alpha[1] * sin(2.0 * M_PI * P.a_freq[1] * py));
     d[2] = P.a_scale[2] * (1.0 - P.a_alpha[2] * sin(2.0 * M_PI * P.a_freq[2] * pz));
     s = expr_eval(prog + P.b_prog_off, P.b_prog_len, px, py, pz);
+    if (P.tensor_inverse) { d[0] = 1.0 / d[0]; d[1] = 1.0 / d[1]; d[2] = 1.0 / d[2]; }
+    if (P.scalar_inverse) s = 1.0 / s;
+    int c = 0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = a; b < 3; ++b) {
+        o[(c++) * kLanes] = P.rot[a * 3 + 0] * d[0] * P.rot[b * 3 + 0] + P.rot[a * 3 + 1] * d[1] * P.rot[b * 3 + 1] +
+                            P.rot[a * 3 + 2] * d[2] * P.rot[b * 3 + 2];
+      }
+    o[6 * kLanes] = s;
   }
-  if (P.tensor_inverse) { d[0] = 1.0 / d[0]; d[1] = 1.0 / d[1]; d[2] = 1.0 / d[2]; }
-  if (P.scalar_inverse) s = 1.0 / s;
-  double *o = coef + ((size_t)(g * P.nC + T) * 56 + q * 7) * kLanes + lane;
-  int c = 0;
-#pragma unroll
-  for (int a = 0; a < 3; ++a)
-#pragma unroll
-    for (int b = a; b < 3; ++b) {
-      o[(c++) * kLanes] = P.rot[a * 3 + 0] * d[0] * P.rot[b * 3 + 0] + P.rot[a * 3 + 1] * d[1] * P.rot[b * 3 + 1] +
-                          P.rot[a * 3 + 2] * d[2] * P.rot[b * 3 + 2];
-    }
-  o[6 * kLanes] = s;
   for (int cc = 0; cc < P.rhs_ncomp; ++cc)
     fr[((size_t)(g * P.nC + T) * (8 * P.rhs_ncomp) + q * P.rhs_ncomp + cc) * kLanes + lane] =
         expr_eval(prog + P.rhs_prog_off[cc], P.rhs_prog_len[cc], px, py, pz);
@@ -738,7 +756,9 @@ class Engine {
       CUDA_OK(cudaFuncSetAttribute(k_direct_update_s<64, 64, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_s_smem<64, 64, 8, 4>()));
       if (const char *b = std::getenv("MSFEC_DIRECT_CHUNK")) direct_chunk_ = std::max(1, std::min(kMaxWindow, std::atoi(b)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_back_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackGemmSmem));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<32>(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
+      if (const char *b = std::getenv("MSFEC_DIRECT_TRSM_ROWS")) trsm_rows_ = std::atoi(b) == 32 ? 32 : 64;
       if (const char *b = std::getenv("MSFEC_DIRECT_LANES")) kDirectLanes = std::max(1, std::min(kMaxDirectLanes, std::atoi(b)));
       {
         // MSFEC_DIRECT_PRIO=1: descending stream priorities (lane 0 highest), so the later lanes fill the gaps
@@ -837,6 +857,7 @@ class Engine {
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
       *d_dp_rhs_ = nullptr, *d_dp_code_ = nullptr;
   bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
+  int trsm_rows_ = 32;                       // rows per CTA of k_direct_trsm (MSFEC_DIRECT_TRSM_ROWS = 32 | 64)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
   // sub-batches can be processed round-robin on several streams ("lanes") with private band storage; measured on
   // B200 this gains nothing (every large kernel fills the GPU and kernels of different streams effectively run
@@ -1107,7 +1128,11 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
             mark("panel");
           }
         }
-        k_direct_trsm<<<dim3((ld - row_hi) / kTR, nc), 128, trsm_smem_bytes(np), stream_>>>(
+        if (trsm_rows_ == 64)
+          k_direct_trsm<64><<<dim3((ld - row_hi + 63) / 64, nc), 128, trsm_smem_bytes<64>(np), stream_>>>(
+            d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+        else
+          k_direct_trsm<32><<<dim3((ld - row_hi) / 32, nc), 128, trsm_smem_bytes<32>(np), stream_>>>(
             d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
         ++launches_;
         mark("trsm");
