@@ -154,6 +154,18 @@ int msfec_set_weights(msfec_ctx *ctx, int n_cells, const double *weights);
  *   (see msfec_fine_dof_layout). Either pointer may be NULL. */
 int msfec_get_fine_solution(msfec_ctx *ctx, int cell, double *block0, double *block1);
 
+/* Squared fine-grid norms of the reconstructed solution of every cell of the last build
+ * (after msfec_set_weights): norms[n_cells][4] = { ||b0||^2_L2, |b0|^2, ||b1||^2_L2, |b1|^2 }
+ * with unit coefficients, |.| the natural semi-norm of the block's element (H1 for nodal,
+ * H(curl) for edge, H(div) for face DoFs; 0 for cell-wise constants), Gauss 2x2x2 per fine
+ * cell.  The reconstruction is linear in the weights, so the norm of the DIFFERENCE of two
+ * multiscale solutions is obtained by passing the difference of their weights to
+ * msfec_set_weights.  The caller sums over cells (and ranks: one FP64 all-reduce, the
+ * error-norm reduction of SURVEY.md s.8(e)) and takes the square root.  The reference
+ * computes no error norm (integrate_difference never appears); this is the harness-defined
+ * norm of the north star.  norms is a host buffer. */
+int msfec_solution_norms(msfec_ctx *ctx, int n_cells, double *norms);
+
 /* Fetch basis function `basis` (0..k_solve-1) of one cell of the last build, full
  * length incl. boundary values (what basis_curl_v / basis_div_v hold). */
 int msfec_get_basis(msfec_ctx *ctx, int cell, int basis, double *block0, double *block1);

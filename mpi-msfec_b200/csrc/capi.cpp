@@ -280,6 +280,14 @@ int msfec_get_fine_solution(msfec_ctx *ctx, int cell, double *block0, double *bl
   return rc ? set_error(ctx, rc, err) : rc;
 }
 
+int msfec_solution_norms(msfec_ctx *ctx, int n_cells, double *norms) {
+  if (int rc = need_engine(ctx)) return rc;
+  if (!norms || n_cells <= 0) return set_error(ctx, MSFEC_EINVAL, "bad argument");
+  std::string err;
+  const int rc = engine_solution_norms(ctx->engine, n_cells, norms, err);
+  return rc ? set_error(ctx, rc, err) : rc;
+}
+
 int msfec_get_basis(msfec_ctx *ctx, int cell, int basis, double *block0, double *block1) {
   if (int rc = need_engine(ctx)) return rc;
   std::string err;
@@ -328,6 +336,17 @@ int msfec_debug_table(const msfec_ctx *ctx, const char *name, void *out, size_t 
   else if (n == "direct.chunk_blk") iv = &dp.chunk_blk; else if (n == "direct.chunk_local") iv = &dp.chunk_local;
   else if (n == "direct.front_pos") iv = &dp.front_pos;
   else if (n == "direct.col_off") { for (auto v : dp.col_off) col_off32.push_back((int32_t)v); iv = &col_off32; }
+  std::vector<NormOperator> nops;
+  std::vector<int32_t> nop_hexp;
+  if (n.rfind("norm", 0) == 0) {          // norm<i>.ptr / .col / .val (i = 0..3), norm.h_exponents
+    nops = build_norm_operators(t);
+    if (n == "norm.h_exponents") { for (auto &o : nops) nop_hexp.push_back(o.h_exponent); iv = &nop_hexp; }
+    for (int i = 0; i < 4; ++i) {
+      const std::string pre = "norm" + std::to_string(i);
+      if (n == pre + ".ptr") iv = &nops[i].ptr; else if (n == pre + ".col") iv = &nops[i].col;
+      else if (n == pre + ".val") dv = &nops[i].val;
+    }
+  }
   if (n == "G") dv = &t.G; else if (n == "F1") dv = &t.F1;
   else if (n == "diag_slot0") iv = &t.diag_slot0; else if (n == "diag_slot1") iv = &t.diag_slot1;
   else if (n == "blk0.cell_dofs") iv = &t.blk[0].cell_dofs; else if (n == "blk1.cell_dofs") iv = &t.blk[1].cell_dofs;

@@ -636,6 +636,41 @@ __global__ void k_combine(int NF, int kg, int n_cells, const double *__restrict_
   U[((size_t)g * NF + d) * kLanes + lane] = acc;
 }
 
+// Squared fine-grid norms of the reconstructed solution: q[cell] = u^T G u with a Gram matrix G shared by all cells
+// (NormOperator, unit h).  U is cell-interleaved [g][NF][32]; block `off`..`off+n` of the DoF range.  Each CTA walks a
+// fixed strided set of rows and its 8 row-warps are summed through shared memory in a fixed order, so the result is
+// deterministic; k_norm_reduce adds the CTA partials (again in a fixed order) and applies h^p.
+// grid (kNormParts, groups), block (32, 8)
+constexpr int kNormParts = 32;
+__global__ void k_norm_partial(int n, const int *__restrict__ ptr, const int *__restrict__ col, const double *__restrict__ val,
+                               const double *__restrict__ U, int NF, int off, double *__restrict__ part) {
+  __shared__ double red[8][kLanes];
+  const int lane = threadIdx.x, w = threadIdx.y, g = blockIdx.y;
+  const double *u = U + ((size_t)g * NF + off) * kLanes + lane;
+  double acc = 0.0;
+  for (int row = blockIdx.x * 8 + w; row < n; row += kNormParts * 8) {
+    double t = 0.0;
+    for (int e = ptr[row]; e < ptr[row + 1]; ++e) t = fma(val[e], u[(size_t)col[e] * kLanes], t);
+    acc = fma(u[(size_t)row * kLanes], t, acc);
+  }
+  red[w][lane] = acc;
+  __syncthreads();
+  if (w == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i][lane];
+    part[((size_t)blockIdx.x * gridDim.y + g) * kLanes + lane] = s;
+  }
+}
+// one thread per cell.  out[cell][4]: column `slot` receives scale * sum of the partials
+__global__ void k_norm_reduce(int n_cells, int groups, const double *__restrict__ part, double scale, int slot, double *__restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cells) return;
+  double s = 0.0;
+  for (int p = 0; p < kNormParts; ++p) s += part[(size_t)p * groups * kLanes + c];
+  out[(size_t)c * 4 + slot] = s * scale;
+}
+
 // Validate corners (axis-aligned cubes of edge H) and scatter origins into the interleaved
 // layout.  One thread per cell of the batch; lanes beyond n_cells replicate the last cell.
 __global__ void k_prepare_cells(const double *__restrict__ corners, const long long *__restrict__ ids, int cell0,
@@ -794,6 +829,8 @@ class Engine {
     sys_.release(); lift_.release(); full_.release(); kint_.release();
     asm00_.release(); asm11_.release(); asmrhs_.release();
     cudaFree(d_diag0_); cudaFree(d_diag1_); cudaFree(d_G_); cudaFree(d_F1_); cudaFree(d_prog_);
+    for (auto &N : norm_) { cudaFree(N.ptr); cudaFree(N.col); cudaFree(N.val); }
+    cudaFree(d_norm_part_); cudaFree(d_norm_out_);
     cudaFree(d_flag_); cudaFreeHost(h_flag_);
     for (auto &ev : ev_) cudaEventDestroy(ev);
     for (auto &ev : ev_sp_) cudaEventDestroy(ev);
@@ -804,6 +841,7 @@ class Engine {
             bool device_ptrs, msfec_stats *stats);
   void set_weights(int n_cells, const double *weights);
   void get_fine_solution(int cell, double *b0, double *b1);
+  void solution_norms(int n_cells, double *norms);
   void get_basis(int cell, int basis, double *b0, double *b1);
   void cell_values(int cell, double *values, size_t *count);
 
@@ -844,6 +882,10 @@ class Engine {
   double *d_Z_ = nullptr, *d_U_ = nullptr, *d_M_ = nullptr, *d_r_ = nullptr, *d_corners_ = nullptr, *d_w_ = nullptr;
   long long *d_ids_ = nullptr;
   bool have_weights_ = false;
+  double H_last_ = 0.0;                      // coarse edge length of the last build
+  struct NormDev { int n = 0, h_exponent = 0; int *ptr = nullptr, *col = nullptr; double *val = nullptr; } norm_[4];
+  bool norms_ready_ = false;
+  double *d_norm_part_ = nullptr, *d_norm_out_ = nullptr;
   int last_batch_cell0_ = 0, last_batch_n_ = 0;
   long launches_ = 0;
   // direct solver
@@ -1224,6 +1266,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   }
   const double H = c0[21] - c0[0];   // vertex 7 - vertex 0, x
   if (!(H > 0)) throw std::invalid_argument("coarse cell 0 has non-positive edge length");
+  H_last_ = H;
   const double h = H / T_.n;
   const double kscale = std::pow(h, T_.k_h_exponent), f1scale = std::pow(H, T_.f1_H_exponent);
   const int cpb = spec_.p.cells_per_batch > 0 ? spec_.p.cells_per_batch : 4096;
@@ -1360,6 +1403,39 @@ void Engine::get_fine_solution(int cell, double *b0, double *b1) {
   if (T_.two_blocks) fetch_strided(d_U_, (g * T_.NF + T_.blk[0].n_total) * kLanes + lane, kLanes, T_.blk[1].n_total, b1);
 }
 
+// norms[cell][4] = { ||b0||^2_L2, |b0|^2_semi, ||b1||^2_L2, |b1|^2_semi } of the reconstructed fine solution, unit
+// coefficients (semi = H1 / H(curl) / H(div) semi-norm of the block's element; 0 where it does not exist).
+void Engine::solution_norms(int n_cells, double *norms) {
+  CUDA_OK(cudaSetDevice(device_));
+  if (!have_weights_) throw std::logic_error("solution_norms: set_weights has not been called");
+  if (n_cells != store_cells_) throw std::invalid_argument("solution_norms: n_cells does not match the last build");
+  if (!norms_ready_) {
+    const std::vector<NormOperator> ops = build_norm_operators(T_);
+    for (int i = 0; i < 4; ++i) {
+      norm_[i].n = ops[i].n; norm_[i].h_exponent = ops[i].h_exponent;
+      if (ops[i].n) { norm_[i].ptr = dev_upload(ops[i].ptr); norm_[i].col = dev_upload(ops[i].col); norm_[i].val = dev_upload(ops[i].val); }
+    }
+    norms_ready_ = true;
+  }
+  const size_t part_bytes = (size_t)kNormParts * store_groups_ * kLanes * sizeof(double);
+  // (re)allocate with the store: sizes follow store_groups_ / store_cells_
+  cudaFree(d_norm_part_); cudaFree(d_norm_out_); d_norm_part_ = d_norm_out_ = nullptr;
+  CUDA_OK(cudaMalloc(&d_norm_part_, part_bytes));
+  CUDA_OK(cudaMalloc(&d_norm_out_, (size_t)n_cells * 4 * sizeof(double)));
+  CUDA_OK(cudaMemsetAsync(d_norm_out_, 0, (size_t)n_cells * 4 * sizeof(double), stream_));
+  const double h = H_last_ / T_.n;
+  for (int i = 0; i < 4; ++i) {
+    if (!norm_[i].n) continue;
+    const int off = i < 2 ? 0 : T_.blk[0].n_total;
+    k_norm_partial<<<dim3(kNormParts, store_groups_), dim3(kLanes, 8), 0, stream_>>>(norm_[i].n, norm_[i].ptr, norm_[i].col, norm_[i].val,
+                                                                                  d_U_, T_.NF, off, d_norm_part_);
+    k_norm_reduce<<<(n_cells + 255) / 256, 256, 0, stream_>>>(n_cells, store_groups_, d_norm_part_, std::pow(h, norm_[i].h_exponent), i, d_norm_out_);
+  }
+  CUDA_OK(cudaMemcpyAsync(norms, d_norm_out_, (size_t)n_cells * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  CUDA_OK(cudaStreamSynchronize(stream_));
+  CUDA_OK(cudaGetLastError());
+}
+
 void Engine::get_basis(int cell, int basis, double *b0, double *b1) {
   CUDA_OK(cudaSetDevice(device_));
   if (!d_Z_ || cell < 0 || cell >= store_cells_) throw std::invalid_argument("cell out of range / no build");
@@ -1411,6 +1487,9 @@ int engine_set_weights(Engine *e, int n_cells, const double *weights, std::strin
 }
 int engine_get_fine_solution(Engine *e, int cell, double *b0, double *b1, std::string &err) {
   GUARD({ e->get_fine_solution(cell, b0, b1); return MSFEC_OK; })
+}
+int engine_solution_norms(Engine *e, int n_cells, double *norms, std::string &err) {
+  GUARD({ e->solution_norms(n_cells, norms); return MSFEC_OK; })
 }
 int engine_get_basis(Engine *e, int cell, int basis, double *b0, double *b1, std::string &err) {
   GUARD({ e->get_basis(cell, basis, b0, b1); return MSFEC_OK; })

@@ -43,6 +43,7 @@ int engine_build(Engine *e, int n_cells, const double *corners, const int64_t *c
                  double *elem_rhs, bool device_ptrs, msfec_stats *stats, std::string &err);
 int engine_set_weights(Engine *e, int n_cells, const double *weights, std::string &err);
 int engine_get_fine_solution(Engine *e, int cell, double *b0, double *b1, std::string &err);
+int engine_solution_norms(Engine *e, int n_cells, double *norms, std::string &err);
 int engine_get_basis(Engine *e, int cell, int basis, double *b0, double *b1, std::string &err);
 int engine_cell_values(Engine *e, int cell, double *values, size_t *count, std::string &err);
 

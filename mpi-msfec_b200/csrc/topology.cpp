@@ -479,6 +479,54 @@ Topology build_topology(int pairing, int n) {
   return t;
 }
 
+std::vector<NormOperator> build_norm_operators(const Topology &t) {
+  std::vector<NormOperator> out(4);
+  for (int b = 0; b < (t.two_blocks ? 2 : 1); ++b) {
+    const BlockTopo &B = t.blk[b];
+    const LocalTables L = local_tables(B.kind);
+    for (int which = 0; which < 2; ++which) {
+      // which = 0: (u, v);  which = 1: (grad u, grad v) / (curl u, curl v) / (div u, div v)
+      FormType type;
+      const double (*vec)[8][3] = nullptr;
+      const double (*sc)[8] = nullptr;
+      int hexp;
+      if (B.kind == ENT_V) { if (!which) { type = FORM_SCALAR; sc = L.sc; hexp = 3; } else { type = FORM_TENSOR; vec = L.vec; hexp = 1; } }
+      else if (B.kind == ENT_E) { type = FORM_TENSOR; if (!which) { vec = L.vec; hexp = 1; } else { vec = L.vec2; hexp = -1; } }
+      else if (B.kind == ENT_F) { if (!which) { type = FORM_TENSOR; vec = L.vec; hexp = -1; } else { type = FORM_SCALAR; sc = L.sc; hexp = -3; } }
+      else { if (which) continue; type = FORM_SCALAR; sc = L.sc; hexp = 3; }
+      AsmTable tab;
+      std::map<std::pair<int, int>, int> slots;
+      build_sym_form(B, t.nC, type, vec, sc, tab, slots);
+      // slot values for the unit coefficient (A = I: channels xx, yy, zz = 1; scalar channel = 1)
+      std::vector<double> v(tab.n_slots, 0.0);
+      for (int s = 0; s < tab.n_slots; ++s) {
+        double acc = 0.0;
+        for (int c = tab.contrib_ptr[s]; c < tab.contrib_ptr[s + 1]; ++c) {
+          const int pr = tab.contrib_pair[c];
+          for (int e = tab.pair_ptr[pr]; e < tab.pair_ptr[pr + 1]; ++e) {
+            const int comp = tab.pair_idx[e] % kCoefPerQ;
+            if (comp == 0 || comp == 3 || comp == 5 || comp == 6) acc += tab.pair_w[e];
+          }
+        }
+        v[s] = acc / 8.0;
+      }
+      NormOperator &op = out[2 * b + which];
+      op.n = B.n_total; op.h_exponent = hexp;
+      op.ptr.assign(op.n + 1, 0);
+      for (auto &kv : slots) { op.ptr[kv.first.first + 1]++; if (kv.first.first != kv.first.second) op.ptr[kv.first.second + 1]++; }
+      for (int r = 0; r < op.n; ++r) op.ptr[r + 1] += op.ptr[r];
+      op.col.resize(op.ptr[op.n]); op.val.resize(op.ptr[op.n]);
+      std::vector<int32_t> fill(op.ptr.begin(), op.ptr.end() - 1);
+      for (auto &kv : slots) {            // std::map iterates (r, c) in lexicographic order: columns ascend per row
+        const int r = kv.first.first, c = kv.first.second;
+        op.col[fill[r]] = c; op.val[fill[r]++] = v[kv.second];
+        if (r != c) { op.col[fill[c]] = r; op.val[fill[c]++] = v[kv.second]; }
+      }
+    }
+  }
+  return out;
+}
+
 }  // namespace msfec
 
 namespace msfec {

@@ -115,6 +115,19 @@ struct DirectPlan {
   double update_flops = 0;                    // FP64 flops of all trailing updates per cell (lower triangle)
 };
 
+// Gram matrix of a fine-grid norm over the DoFs of ONE block (interior-first numbering), CSR, identical for
+// every coarse cell up to the factor h^h_exponent (values include the 1/8 quadrature weight of the unit cube).
+// The reference computes no error norm (integrate_difference never appears); these define the harness norms of
+// the north star: L2 and the natural semi-norm of each field with unit coefficients, Gauss 2x2x2 on every fine cell.
+struct NormOperator {
+  int n = 0, h_exponent = 0;
+  std::vector<int32_t> ptr, col;
+  std::vector<double> val;
+};
+// [2 b + 0]: L2 Gram of block b;  [2 b + 1]: |.|_H1 (vertices), |.|_H(curl) (edges), |.|_H(div) (faces), empty for
+// cell-wise constants.  Entries of a missing block are empty (n = 0).
+std::vector<NormOperator> build_norm_operators(const Topology &t);
+
 // Builds everything above.  pairing: enum msfec_pairing; n = 2^L.
 Topology build_topology(int pairing, int n);
 // ordering: 0 = split layers/planes (default), 1 = slabs

@@ -109,6 +109,18 @@ void BasisBatch::fine_solution(int cell, std::vector<double> &b0, std::vector<do
   if (msfec_get_fine_solution(ctx_, cell, b0.data(), n1 ? b1.data() : nullptr)) throw std::runtime_error(msfec_last_error(ctx_));
 }
 
+std::array<double, 4> BasisBatch::solution_norms_squared() {
+  if (weights_dirty_) {
+    if (msfec_set_weights(ctx_, (int)ids_.size(), w_.data())) throw std::runtime_error(msfec_last_error(ctx_));
+    weights_dirty_ = false;
+  }
+  std::vector<double> per_cell(ids_.size() * 4);
+  if (msfec_solution_norms(ctx_, (int)ids_.size(), per_cell.data())) throw std::runtime_error(msfec_last_error(ctx_));
+  std::array<double, 4> sum{0, 0, 0, 0};
+  for (size_t c = 0; c < ids_.size(); ++c) for (int i = 0; i < 4; ++i) sum[i] += per_cell[4 * c + i];
+  return sum;
+}
+
 void BasisBatch::basis_function(int cell, int index, std::vector<double> &b0, std::vector<double> &b1) {
   int n0 = 0, n1 = 0;
   msfec_n_fine_dofs(pairing_, L_, &n0, &n1);

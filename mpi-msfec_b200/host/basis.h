@@ -42,6 +42,10 @@ class BasisBatch {
   const double *rhs(int cell) const { return &r_[(size_t)cell * k_]; }
   void set_weights(int cell, const std::vector<double> &w);
   void fine_solution(int cell, std::vector<double> &b0, std::vector<double> &b1);
+  // Sum over this rank's cells of the squared fine-grid norms of the solution set by set_weights: L2 and natural
+  // semi-norm (H1 / H(curl) / H(div)) of block 0, then of block 1 (msfec_solution_norms).  Ranks add these four
+  // numbers (MPI_Allreduce / ncclAllReduce, sum, FP64) and take square roots.
+  std::array<double, 4> solution_norms_squared();
   void basis_function(int cell, int index, std::vector<double> &b0, std::vector<double> &b1);
   // VTU (ParaView) file of fine-grid data of one coarse cell: what output_global_solution_in_cell /
   // output_basis write through deal.II DataOut (ned_rt_basis.cc:951-1031, 1092-1147).  Vector fields are

@@ -61,7 +61,7 @@ EXPORTS = [
     "msfec_abi_version", "msfec_problem_defaults", "msfec_problem_from_prm", "msfec_problem_free", "msfec_k",
     "msfec_n_fine_dofs", "msfec_create", "msfec_destroy", "msfec_last_error", "msfec_build_basis",
     "msfec_build_basis_device", "msfec_set_weights", "msfec_get_fine_solution", "msfec_get_basis",
-    "msfec_fine_dof_layout", "msfec_debug_table", "msfec_debug_cell_values",
+    "msfec_solution_norms", "msfec_fine_dof_layout", "msfec_debug_table", "msfec_debug_cell_values",
 ]
 
 _lib = None
@@ -86,6 +86,7 @@ def lib():
         L.msfec_set_weights.argtypes = [vp, C.c_int, vp]
         L.msfec_get_fine_solution.argtypes = [vp, C.c_int, vp, vp]
         L.msfec_get_basis.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+        L.msfec_solution_norms.argtypes = [vp, C.c_int, vp]
         L.msfec_fine_dof_layout.argtypes = [vp, C.c_int, vp, vp, vp]
         L.msfec_debug_table.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_size_t), C.POINTER(C.c_int)]
         L.msfec_debug_cell_values.argtypes = [vp, C.c_int, vp, C.POINTER(C.c_size_t)]
@@ -188,6 +189,13 @@ class BasisBuilder:
         b0 = np.empty(self.n_block[0]); b1 = np.empty(self.n_block[1]) if self.n_block[1] else None
         self._check(lib().msfec_get_fine_solution(self._ctx, cell, _ptr(b0), _ptr(b1)))
         return b0, b1
+
+    def solution_norms(self, n_cells: int) -> np.ndarray:
+        """[n_cells, 4] squared norms (L2 / semi-norm of block 0, L2 / semi-norm of block 1) of the fine solution
+        reconstructed by set_global_weights, summed on the device per cell (msfec_solution_norms)."""
+        out = np.empty((n_cells, 4))
+        self._check(lib().msfec_solution_norms(self._ctx, n_cells, _ptr(out)))
+        return out
 
     def get_basis(self, cell: int, basis: int):
         b0 = np.empty(self.n_block[0]); b1 = np.empty(self.n_block[1]) if self.n_block[1] else None

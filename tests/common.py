@@ -37,3 +37,18 @@ def lib_problem(msfec, pairing, L, random_seed=0, **kw):
 
 def rel_err(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-300))
+
+
+KINDS = {"Q": ("V", None), "Q_NED": ("V", "E"), "NED_RT": ("E", "F"), "RT_DQ": ("F", "C")}
+
+
+def perm_to_oracle(bb, prob, block, kind):
+    """library fine-DoF index -> oracle fine-DoF index of one block (matched by position)."""
+    g = mo.fine_grid(prob.n)
+    opos = {"V": g.v_pos, "E": g.e_pos, "F": g.f_pos, "C": None}[kind]
+    pos, axis, bnd = bb.layout(block)
+    if kind == "C":
+        n = prob.n
+        return (np.floor(pos[:, 0]) + n * (np.floor(pos[:, 1]) + n * np.floor(pos[:, 2]))).astype(int)
+    key = {tuple(np.round(p * 2).astype(int)): i for i, p in enumerate(opos)}
+    return np.array([key[tuple(np.round(p * 2).astype(int))] for p in pos])

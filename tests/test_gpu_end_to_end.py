@@ -6,24 +6,10 @@ import numpy as np
 import pytest
 
 import coarse_solve as cs
-from common import lib_problem, oracle_problem, rel_err
+from common import KINDS, lib_problem, oracle_problem, perm_to_oracle as _perm_to_oracle, rel_err
 from oracle import msfec_oracle as mo
 
 pytestmark = pytest.mark.gpu
-
-
-def _perm_to_oracle(bb, prob, block, kind):
-    g = mo.fine_grid(prob.n)
-    opos = {"V": g.v_pos, "E": g.e_pos, "F": g.f_pos, "C": None}[kind]
-    pos, axis, bnd = bb.layout(block)
-    if kind == "C":
-        n = prob.n
-        return (np.floor(pos[:, 0]) + n * (np.floor(pos[:, 1]) + n * np.floor(pos[:, 2]))).astype(int)
-    key = {tuple(np.round(p * 2).astype(int)): i for i, p in enumerate(opos)}
-    return np.array([key[tuple(np.round(p * 2).astype(int))] for p in pos])
-
-
-KINDS = {"Q": ("V", None), "Q_NED": ("V", "E"), "NED_RT": ("E", "F"), "RT_DQ": ("F", "C")}
 
 
 @pytest.mark.parametrize("direct", [1, 0], ids=["direct", "minres"])
@@ -78,3 +64,46 @@ def test_final_multiscale_solution_matches_oracle(msfec, pairing, direct):
         rel = np.sqrt(num[name] / max(den[name], 1e-300))
         print(pairing, "direct" if direct else "minres", name, "relative difference", rel)
         assert rel < 1e-8, (name, rel)
+
+
+NORM_NAMES = {"Q": ("sigma_L2", "sigma_H1semi", None, None),
+              "Q_NED": ("sigma_L2", "sigma_H1semi", "u_L2", "u_Hcurlsemi"),
+              "NED_RT": ("sigma_L2", "sigma_Hcurlsemi", "u_L2", "u_Hdivsemi"),
+              "RT_DQ": ("sigma_L2", "sigma_Hdivsemi", None, None)}
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_device_solution_norms_match_harness(msfec, pairing):
+    """msfec_solution_norms (device reduction of u^T G u per cell) against the harness' Gram matrices, and the
+    difference-of-weights route to the norm of the difference of two multiscale solutions."""
+    g_ref, L = 2, 2
+    cells = mo.morton_cells(g_ref)[:40]              # ragged: one full group of 32 + 8
+    ids = np.arange(len(cells))
+    prob = oracle_problem(pairing, L)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L), device=0).run(cells, ids)
+    k = bb.get_global_element_matrix().shape[1]
+    rng = np.random.default_rng(5)
+    w_a = rng.standard_normal((len(cells), k)); w_b = w_a + 1e-6 * rng.standard_normal((len(cells), k))
+    norms = cs.unit_norm_matrices(pairing, L, cells[0])
+    p0 = _perm_to_oracle(bb, prob, 0, KINDS[pairing][0])
+    p1 = _perm_to_oracle(bb, prob, 1, KINDS[pairing][1]) if KINDS[pairing][1] else None
+    h = (cells[0][7][0] - cells[0][0][0]) / prob.n
+    for w in (w_a, w_a - w_b):
+        bb.set_global_weights(w)
+        dev = bb.solution_norms(len(cells))
+        assert dev.shape == (len(cells), 4) and (dev >= 0).all()
+        for c in (0, 17, 31, 32, 39):
+            s_gpu, u_gpu = bb.get_fine_solution(c)
+            s_o = np.empty_like(s_gpu); s_o[p0] = s_gpu
+            if p1 is not None:
+                u_o = np.empty_like(u_gpu); u_o[p1] = u_gpu
+            for slot, name in enumerate(NORM_NAMES[pairing]):
+                if name is None:
+                    continue
+                v = s_o if slot < 2 else u_o
+                ref = v @ (norms[name] @ v)
+                assert abs(dev[c, slot] - ref) <= 1e-11 * max(abs(ref), 1e-300), (pairing, c, name, dev[c, slot], ref)
+            if pairing == "RT_DQ":                   # cell-wise constants: ||u||^2 = h^3 sum u^2, no semi-norm
+                assert abs(dev[c, 2] - h ** 3 * (u_gpu ** 2).sum()) <= 1e-11 * dev[c, 2] and dev[c, 3] == 0.0
+            if pairing == "Q":
+                assert dev[c, 2] == 0.0 and dev[c, 3] == 0.0

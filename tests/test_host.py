@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import emulate
-from common import ROOT, lib_problem, oracle_problem, prm_path, rel_err
+from common import KINDS, ROOT, lib_problem, oracle_problem, perm_to_oracle, prm_path, rel_err
 from oracle import msfec_oracle as mo
 
 
@@ -150,3 +150,34 @@ def test_direct_plan_tables(msfec, pairing, L):
     # block structure sanity: every block column's front starts with itself; sizes are multiples of 32
     bs = bb.table("direct.bs"); ch_off = bb.table("direct.chunk_off"); ch_blk = bb.table("direct.chunk_blk")
     assert (bs % 32 == 0).all() and all(ch_blk[ch_off[s]] == s and ch_blk[ch_off[s + 1] - 1] == -1 for s in range(len(bs)))
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_norm_operator_tables_match_oracle_gram_matrices(msfec, pairing):
+    """The Gram matrices msfec_solution_norms applies on the device (csrc/topology.cpp:build_norm_operators) equal the
+    oracle's unit-coefficient mass / grad-grad / curl-curl / div-div matrices."""
+    import scipy.sparse as sp
+    import coarse_solve as cs
+    L = 2
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L), device=-1)
+    prob = oracle_problem(pairing, L)
+    cells = mo.morton_cells(2)
+    h = (cells[0][7][0] - cells[0][0][0]) / prob.n
+    ref = cs.unit_norm_matrices(pairing, L, cells[0])
+    hexp = bb.table("norm.h_exponents")
+    names = {"Q": ("sigma_L2", "sigma_H1semi", None, None), "Q_NED": ("sigma_L2", "sigma_H1semi", "u_L2", "u_Hcurlsemi"),
+             "NED_RT": ("sigma_L2", "sigma_Hcurlsemi", "u_L2", "u_Hdivsemi"), "RT_DQ": ("sigma_L2", "sigma_Hdivsemi", "cells", None)}[pairing]
+    for i, name in enumerate(names):
+        ptr = bb.table(f"norm{i}.ptr")
+        if name is None:
+            assert len(ptr) == 0 or ptr[-1] == 0
+            continue
+        n = len(ptr) - 1
+        G = sp.csr_matrix((bb.table(f"norm{i}.val") * h ** float(hexp[i]), bb.table(f"norm{i}.col"), ptr), shape=(n, n))
+        if name == "cells":
+            assert abs(G - sp.identity(n) * h ** 3).max() < 1e-18
+            continue
+        p = perm_to_oracle(bb, prob, i // 2, KINDS[pairing][i // 2])
+        Go = sp.csr_matrix(ref[name])[p][:, p]
+        assert abs(G - Go).max() <= 1e-13 * abs(Go).max(), (pairing, name)
+        assert abs(G - G.T).max() == 0.0
