@@ -171,6 +171,333 @@ k_direct_diag(const double *__restrict__ band, size_t band_stride, long long col
   for (int k = 0; k < kDP; ++k) vo[(size_t)k * kDP + lane] = Ls[w][lane][k];   // column-major: V(n = lane, k)
 }
 
+// ---- fused factorisation of a chunk's diagonal region --------------------------------------
+// One launch per chunk instead of (diag, panel, strip update) per 32-column panel: ONE WARP per cell factors the
+// whole (32 np) x (32 np) lower-triangular region right-looking, lane = row of the current 32 x 32 block:
+//   for p:  LDL^T of block (p,p) in registers (the pivot column is broadcast through shared memory: 16 LDS.128 per
+//           step instead of 62 SHFL; the per-panel kernel was bound by the shuffle unit), pivots -> dvec, V_p = L^-1 -> vinv;
+//           blocks (q,p), q > p:  X = A L_pp^-T by forward substitution, L = X D^-1 back to the band;
+//           blocks (q',q), p < q <= q':  C -= X_q'p L_qp^T  (L_qp rows broadcast from shared memory).
+// No block-wide barriers (warps are independent), FP64 FMA pipe only.  The band keeps L in the sub-diagonal blocks
+// (what k_direct_trsm / k_direct_back_diag read); the diagonal blocks themselves are never read again.
+// grid (ceil(cells/kRegionWarps)), block 32 kRegionWarps
+constexpr int kRLd = kDP + 2;   // shared-memory row stride: even, so that (k, k+1) pairs load as 16 bytes
+constexpr int kRegionWarps = 2; // cells per CTA (17.8 KB of static shared memory per warp)
+__global__ void __launch_bounds__(32 * kRegionWarps, 6)
+k_direct_region(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int np, int pglob0, int NP,
+                int n_cells, double *__restrict__ dvec, double *__restrict__ vinv, int *__restrict__ bad) {
+  __shared__ __align__(16) double Ls_[kRegionWarps][kDP][kRLd];   // rows of L_pp (strictly lower part, zeros elsewhere)
+  __shared__ __align__(16) double Lq_[kRegionWarps][kDP][kRLd];   // rows of L_qp for the in-region updates; V staging
+  __shared__ __align__(16) double colb_[kRegionWarps][2][kDP];    // pivot-column broadcast, double buffered
+  __shared__ __align__(16) double dsm_[kRegionWarps][2][kDP];     // [0]: 1/d, [1]: d of the current panel
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cell = blockIdx.x * kRegionWarps + w;
+  if (cell >= n_cells) return;                          // warp-uniform
+  double (*Ls)[kRLd] = Ls_[w];
+  double (*Lq)[kRLd] = Lq_[w];
+  double *P = band + (size_t)cell * band_stride + col_off;
+  for (int p = 0; p < np; ++p) {
+    const int jp = j0 + p * kDP;                        // first column / row of block (p,p) in the block column
+    // ---- LDL^T of the diagonal block -----------------------------------------------------------
+    double a[kDP];
+#pragma unroll
+    for (int k = 0; k < kDP; ++k) a[k] = (k <= lane) ? P[(size_t)(jp + k) * ld + jp + lane] : 0.0;
+    double my_d = 0.0;
+#pragma unroll
+    for (int c = 0; c < kDP; ++c) {
+      double *cb = colb_[w][c & 1];
+      cb[lane] = a[c];                                  // unscaled column c, one entry per lane (row)
+      __syncwarp();
+      const double d = cb[c];
+      const double dinv = 1.0 / d;
+      const double l = a[c] * dinv;
+      if (lane == c) {
+        my_d = d;
+        if (!(fabs(d) > 1e-300) || !isfinite(d)) atomicExch(bad, 1);
+      }
+#pragma unroll
+      for (int jj = (c + 1) / 2; jj < kDP / 2; ++jj) {
+        const double2 v = reinterpret_cast<const double2 *>(cb)[jj];
+        if (2 * jj > c && 2 * jj <= lane) a[2 * jj] = fma(-l, v.x, a[2 * jj]);
+        if (2 * jj + 1 > c && 2 * jj + 1 <= lane) a[2 * jj + 1] = fma(-l, v.y, a[2 * jj + 1]);
+      }
+      if (lane > c) a[c] = l;
+    }
+    dvec[(size_t)cell * NP + pglob0 + p * kDP + lane] = my_d;
+    dsm_[w][0][lane] = 1.0 / my_d;
+    dsm_[w][1][lane] = my_d;
+#pragma unroll
+    for (int k = 0; k < kDP; ++k) Ls[lane][k] = (k < lane) ? a[k] : 0.0;
+    __syncwarp();
+    // ---- V_p = L_pp^-1: lane j solves L v = e_j (column j of V) ----------------------------------
+    {
+      double v[kDP];
+#pragma unroll
+      for (int i = 0; i < kDP; ++i) {
+        double t = (i == lane) ? 1.0 : 0.0, t2 = 0.0;      // two partial sums: shorter dependent FMA chains
+#pragma unroll
+        for (int kk = 0; kk < i / 2; ++kk) {
+          const double2 lv = *reinterpret_cast<const double2 *>(&Ls[i][2 * kk]);
+          t = fma(-lv.x, v[2 * kk], t);
+          t2 = fma(-lv.y, v[2 * kk + 1], t2);
+        }
+        if (i & 1) t = fma(-Ls[i][i - 1], v[i - 1], t);
+        v[i] = t + t2;
+        asm volatile("" ::: "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < kDP; ++i) Lq[i][lane] = v[i];                 // Lq[i][j] = V(i, j)
+      __syncwarp();
+      double *vo = vinv + ((size_t)cell * NP + pglob0 + p * kDP) * kDP;
+#pragma unroll
+      for (int k = 0; k < kDP; ++k) vo[(size_t)k * kDP + lane] = Lq[lane][k];   // column-major: V(n = lane, k)
+      __syncwarp();
+    }
+    if (p + 1 == np) break;
+    // ---- blocks below: X = A L_pp^-T, L = X D^-1 ---------------------------------------------------
+    for (int q = p + 1; q < np; ++q) {
+      double *B = P + (size_t)jp * ld + j0 + q * kDP + lane;             // row `lane` of block (q, p)
+      double y[kDP];
+#pragma unroll
+      for (int k = 0; k < kDP; ++k) y[k] = B[(size_t)k * ld];
+#pragma unroll
+      for (int k = 1; k < kDP; ++k) {
+        double t = y[k], t2 = 0.0;
+#pragma unroll
+        for (int mm = 0; mm < k / 2; ++mm) {
+          const double2 lv = *reinterpret_cast<const double2 *>(&Ls[k][2 * mm]);
+          t = fma(-y[2 * mm], lv.x, t);
+          t2 = fma(-y[2 * mm + 1], lv.y, t2);
+        }
+        if (k & 1) t = fma(-y[k - 1], Ls[k][k - 1], t);
+        y[k] = t + t2;
+        asm volatile("" ::: "memory");
+      }
+#pragma unroll
+      for (int k = 0; k < kDP; ++k) B[(size_t)k * ld] = y[k] * dsm_[w][0][k];
+    }
+    __syncwarp();                                        // the L blocks written above are re-read by other lanes
+    // ---- right-looking update of the rest of the region ---------------------------------------------
+    for (int q = p + 1; q < np; ++q) {
+      {
+        const double *B = P + (size_t)jp * ld + j0 + q * kDP + lane;     // row `lane` of L_qp
+#pragma unroll
+        for (int k = 0; k < kDP; ++k) Lq[lane][k] = B[(size_t)k * ld];
+      }
+      __syncwarp();
+      for (int q2 = q; q2 < np; ++q2) {
+        const double *B = P + (size_t)jp * ld + j0 + q2 * kDP + lane;    // row `lane` of L_q2p
+        double x[kDP];
+#pragma unroll
+        for (int k = 0; k < kDP; ++k) x[k] = B[(size_t)k * ld] * dsm_[w][1][k];     // X = L D
+        double *C = P + (size_t)(j0 + q * kDP) * ld + j0 + q2 * kDP + lane;         // row `lane` of block (q2, q)
+        // 4 target columns at a time: 4 independent FMA chains, each L_qp pair is one 16-byte broadcast load
+#pragma unroll 2
+        for (int jb = 0; jb < kDP; jb += 4) {
+          double t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) t[u] = C[(size_t)(jb + u) * ld];
+#pragma unroll
+          for (int kk = 0; kk < kDP / 2; ++kk) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const double2 lv = *reinterpret_cast<const double2 *>(&Lq[jb + u][2 * kk]);
+              t[u] = fma(-x[2 * kk], lv.x, t[u]);
+              t[u] = fma(-x[2 * kk + 1], lv.y, t[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) C[(size_t)(jb + u) * ld] = t[u];
+        }
+      }
+      __syncwarp();                                      // Lq is restaged for the next q
+    }
+    __syncwarp();                                        // updated blocks are re-read with other lane mappings
+  }
+}
+
+// Same factorisation with the block products on the FP64 tensor cores (the FMA version above is bound by the shared-
+// memory return path: every FMA needs a broadcast operand).  One warp per CTA; per panel p:
+//   LDL^T of block (p,p) in registers (pivot column broadcast through shared memory), V_p = L_pp^-1 (lane = column);
+//   X_qp = A_qp V_p^T for the blocks below as one 32x32x32 DMMA product each (zero k-steps of the triangular V_p
+//   skipped), L = X D^-1 to the band, X kept in shared memory;
+//   C(q2,q) -= X_q2p L_qp^T on DMMA with L = X D^-1 formed in the fragment load; diagonal targets skip the 8x8 tiles
+//   above the diagonal.
+// MMA m = band column, n = band row, so accumulator pairs are consecutive band rows (16-byte global accesses).
+// Shared memory: max(np, 2) blocks of 32 x 36 doubles (V_p + one per block row below; the first of those holds the
+// rows of L_pp while V_p is computed).   grid (cells), block 32, dynamic shared memory region_mma_smem(np)
+constexpr int kRMLd = kDP + 4;                     // row stride 36 = 4 mod 16: conflict-free fragment loads
+constexpr size_t region_mma_smem(int np) { return ((size_t)(np < 2 ? 2 : np) * kDP * kRMLd + 3 * kDP) * sizeof(double); }
+
+__device__ __forceinline__ double rcp_newton(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));   // ~2^-20; three Newton steps give full double precision
+  r = fma(fma(-d, r, 1.0), r, r);
+  r = fma(fma(-d, r, 1.0), r, r);
+  r = fma(fma(-d, r, 1.0), r, r);
+  return r;
+}
+
+__global__ void __launch_bounds__(32, 8)
+k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int np, int pglob0,
+                    int NP, double *__restrict__ dvec, double *__restrict__ vinv, int *__restrict__ bad) {
+  extern __shared__ __align__(16) double rm_smem[];
+  double *Vs = rm_smem;                                   // [32][36]  V_p(i, j)
+  double *S1 = rm_smem + kDP * kRMLd;                     // [np-1][32][36]  L_pp rows, then X blocks of rows q > p
+  double *colb = rm_smem + (size_t)(np < 2 ? 2 : np) * kDP * kRMLd;      // [2][32]
+  double *dsm = colb + 2 * kDP;                           // [32]  1/d of the current panel
+  const int cell = blockIdx.x, lane = threadIdx.x;
+  const int fr = lane >> 2, fk = lane & 3;
+  double *P = band + (size_t)cell * band_stride + col_off;
+  for (int p = 0; p < np; ++p) {
+    const int jp = j0 + p * kDP;
+    // ---- LDL^T of the diagonal block, lane = row ---------------------------------------------------
+    double my_d = 0.0;
+    {
+      double a[kDP];
+#pragma unroll
+      for (int k = 0; k < kDP; ++k) a[k] = (k <= lane) ? P[(size_t)(jp + k) * ld + jp + lane] : 0.0;
+#pragma unroll
+      for (int c = 0; c < kDP; ++c) {
+        double *cb = colb + (c & 1) * kDP;
+        cb[lane] = a[c];
+        __syncwarp();
+        const double d = cb[c];
+        const double l = a[c] * rcp_newton(d);
+        if (lane == c) {
+          my_d = d;
+          if (!(fabs(d) > 1e-300) || !isfinite(d)) atomicExch(bad, 1);
+        }
+#pragma unroll
+        for (int jj = (c + 1) / 2; jj < kDP / 2; ++jj) {
+          const double2 v = reinterpret_cast<const double2 *>(cb)[jj];
+          if (2 * jj > c && 2 * jj <= lane) a[2 * jj] = fma(-l, v.x, a[2 * jj]);
+          if (2 * jj + 1 > c && 2 * jj + 1 <= lane) a[2 * jj + 1] = fma(-l, v.y, a[2 * jj + 1]);
+        }
+        if (lane > c) a[c] = l;
+      }
+      dvec[(size_t)cell * NP + pglob0 + p * kDP + lane] = my_d;
+      dsm[lane] = 1.0 / my_d;
+#pragma unroll
+      for (int k = 0; k < kDP; ++k) S1[lane * kRMLd + k] = (k < lane) ? a[k] : 0.0;
+    }
+    __syncwarp();
+    // ---- V_p = L_pp^-1: lane j solves L v = e_j ------------------------------------------------------
+    {
+      double v[kDP];
+#pragma unroll
+      for (int i = 0; i < kDP; ++i) {
+        double t = (i == lane) ? 1.0 : 0.0, t2 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < i / 2; ++kk) {
+          const double2 lv = *reinterpret_cast<const double2 *>(&S1[i * kRMLd + 2 * kk]);
+          t = fma(-lv.x, v[2 * kk], t);
+          t2 = fma(-lv.y, v[2 * kk + 1], t2);
+        }
+        if (i & 1) t = fma(-S1[i * kRMLd + i - 1], v[i - 1], t);
+        v[i] = t + t2;
+        asm volatile("" ::: "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < kDP; ++i) Vs[i * kRMLd + lane] = v[i];
+    }
+    __syncwarp();
+    {
+      double *vo = vinv + ((size_t)cell * NP + pglob0 + p * kDP) * kDP;
+#pragma unroll
+      for (int k = 0; k < kDP; ++k) vo[(size_t)k * kDP + lane] = Vs[lane * kRMLd + k];   // column-major V(n = lane, k)
+    }
+    if (p + 1 == np) break;
+    double dinv_m[4], ndinv_k[kDP / 4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dinv_m[t] = dsm[t * 8 + fr];
+#pragma unroll
+    for (int ks = 0; ks < kDP / 4; ++ks) ndinv_k[ks] = -dsm[ks * 4 + fk];
+    // ---- blocks below: X_qp = A_qp V_p^T ----------------------------------------------------------------
+    for (int q = p + 1; q < np; ++q) {
+      double *Xq = S1 + (size_t)(q - p - 1) * kDP * kRMLd;
+      {
+        const double *B = P + (size_t)jp * ld + j0 + q * kDP + lane;       // row `lane` of A_qp
+#pragma unroll
+        for (int k = 0; k < kDP; ++k) Xq[lane * kRMLd + k] = B[(size_t)k * ld];
+      }
+      __syncwarp();
+      double acc[4][4][2];
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+#pragma unroll
+      for (int ks = 0; ks < kDP / 4; ++ks) {
+        double bf[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bf[t] = Xq[(t * 8 + fr) * kRMLd + ks * 4 + fk];        // B[k = m'][n = i] = A(i, m')
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          if (ks >= 2 * mt + 2) continue;                                                   // V(k, m') = 0 for m' > k
+          const double af = Vs[(mt * 8 + fr) * kRMLd + ks * 4 + fk];                        // A[m = k][k = m'] = V(k, m')
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af, bf[nt]);
+        }
+      }
+      __syncwarp();                                                          // A_qp fully consumed: overwrite with X_qp
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int k = mt * 8 + fr, i = nt * 8 + fk * 2;
+          Xq[i * kRMLd + k] = acc[mt][nt][0];
+          Xq[(i + 1) * kRMLd + k] = acc[mt][nt][1];
+          *reinterpret_cast<double2 *>(P + (size_t)(jp + k) * ld + j0 + q * kDP + i) =
+              make_double2(acc[mt][nt][0] * dinv_m[mt], acc[mt][nt][1] * dinv_m[mt]);
+        }
+    }
+    __syncwarp();
+    // ---- right-looking update of the rest of the region: C(q2, q) -= X_q2p L_qp^T ----------------------------
+    for (int q = p + 1; q < np; ++q) {
+      const double *Lq = S1 + (size_t)(q - p - 1) * kDP * kRMLd;            // X_qp; L = X D^-1 in the fragment load
+      for (int q2 = q; q2 < np; ++q2) {
+        const double *Xq2 = S1 + (size_t)(q2 - p - 1) * kDP * kRMLd;
+        double *C = P + (size_t)(j0 + q * kDP + fr) * ld + j0 + q2 * kDP + fk * 2;
+        const bool dg = q2 == q;
+        double acc[4][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if (dg && nt < mt) continue;
+            const double2 v = *reinterpret_cast<const double2 *>(C + (size_t)(mt * 8) * ld + nt * 8);
+            acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
+          }
+#pragma unroll
+        for (int ks = 0; ks < kDP / 4; ++ks) {
+          double af[4], bf[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            af[t] = Lq[(t * 8 + fr) * kRMLd + ks * 4 + fk] * ndinv_k[ks];                   // A[m = j][k] = -L(j, k)
+            bf[t] = Xq2[(t * 8 + fr) * kRMLd + ks * 4 + fk];                                // B[k][n = i] = X(i, k)
+          }
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              if (dg && nt < mt) continue;
+              dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            if (dg && nt < mt) continue;
+            *reinterpret_cast<double2 *>(C + (size_t)(mt * 8) * ld + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+          }
+      }
+    }
+    __syncwarp();                                          // next panel re-reads band and shared memory with other lane mappings
+  }
+}
+
 // Row-parallel triangular solve of the virtual rows v in [j0+32, ld) (rest of slab s, slab s+1 and the rhs
 // rows: forward substitution is fused into the factorisation) against the factored diagonal block.
 // grid (ceil(nrows/128), cells), block 128
@@ -440,6 +767,7 @@ k_direct_update_s(double *__restrict__ band, size_t band_stride, DirectPlanDev D
   const int fr = lane >> 2, fk = lane & 3;
   const int vc0 = cbase + wc * 32, vr0 = rbase + wr * 32;
   const bool active = vc0 < vc_hi && vc0 < front_rows && vr0 >= vc0 && vr0 < ld;
+  const bool diagw = vr0 == vc0;
   double *cdst = cb;
   int ldc = ld;
   if (active) {
@@ -482,10 +810,18 @@ k_direct_update_s(double *__restrict__ band, size_t band_stride, DirectPlanDev D
           af[t] = Ys[kk * LDY + t * 8];
           bf[t] = Ls[kk * LDL + t * 8];
         }
+        if (diagw) {
+          // warp tile on the diagonal: 8x8 sub-tiles strictly above it (row tile nt < column tile mt) are never read
 #pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
+          for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
-          for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            for (int nt = mt; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        } else {
+#pragma unroll
+          for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
       }
     }
   }
@@ -514,7 +850,7 @@ k_direct_update_s(double *__restrict__ band, size_t band_stride, DirectPlanDev D
 constexpr int kTBs = kDP + 4;
 template <int TR>
 constexpr size_t trsm_smem_bytes(int np) {
-  return ((size_t)np * kDP * (TR + 4) + 3 * kDP * kTBs + kDP * (TR + 4) + (size_t)np * kDP) * sizeof(double);
+  return ((size_t)np * kDP * (TR + 4) + 3 * kDP * kTBs + (size_t)np * kDP) * sizeof(double);
 }
 
 // TR rows per CTA (32 or 64): a warp owns 16 columns x TR/2 rows of the current panel.  TR = 64 halves the number
@@ -529,8 +865,7 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
   extern __shared__ __align__(16) double trsm_smem[];
   double *Xs = trsm_smem;                                  // [32 np][kTLd]   A, then X
   double *Bs = Xs + (size_t)np * kDP * kTLd;               // [3][32][kTBs]   operand ring, [k][n]
-  double *Ts = Bs + 3 * kDP * kTBs;                        // [32][kTLd]      T_p as MMA operand
-  double *dinv = Ts + kDP * kTLd;                          // [32 np]
+  double *dinv = Bs + 3 * kDP * kTBs;                      // [32 np]
   const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = row_lo + blockIdx.x * TR;
   double *P = band + (size_t)cell * band_stride + col_off;
@@ -566,8 +901,11 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
     if (b < nblk) { stage_blk(b, sp, sq); advance(sp, sq); }
     cp_async_commit();
   }
-  const int wm = warp >> 1, wn = warp & 1;                 // wm: column half (MMA m), wn: row half (MMA n)
+  const int wm = warp >> 1, wn = warp & 1;                 // wm: column tiles (MMA m), wn: row half (MMA n)
   const int fr = lane >> 2, fk = lane & 3;
+  // a warp owns the 8-column tiles {wm, 3 - wm} of the panel: V_p is lower triangular, so tile t needs only the
+  // k-steps below 8 (t + 1); pairing tile t with 3 - t gives both warps 10 of the 16 k-steps (5/8 of the MMAs)
+  const int m0[2] = {wm * 8, (3 - wm) * 8};
   const bool rows_valid = r0 + wn * WR < ld;               // warp-uniform (valid rows come in multiples of 32)
   double acc[2][NTL][2];
   int p = 0, q = 0;
@@ -576,14 +914,14 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
     __syncthreads();
     if (b + 2 < nblk) { stage_blk(b + 2, sp, sq); advance(sp, sq); }
     cp_async_commit();
-    const double *Bb = Bs + (size_t)(b % 3) * kDP * kTBs + wm * 16 + fr;
+    const double *Bb = Bs + (size_t)(b % 3) * kDP * kTBs + fr;
     if (q == 0 && p > 0) {
       // acc := A_p (own 16 columns x WR rows)
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) {
-          const double2 v = *reinterpret_cast<const double2 *>(Xs + (size_t)(p * kDP + wm * 16 + mt * 8 + fr) * kTLd + wn * WR + nt * 8 + fk * 2);
+          const double2 v = *reinterpret_cast<const double2 *>(Xs + (size_t)(p * kDP + m0[mt] + fr) * kTLd + wn * WR + nt * 8 + fk * 2);
           acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
         }
     }
@@ -595,7 +933,7 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
         const int kk = ks * 4 + fk;
         double af[2], bf[NTL];
 #pragma unroll
-        for (int t = 0; t < 2; ++t) af[t] = -Bb[kk * kTBs + t * 8];
+        for (int t = 0; t < 2; ++t) af[t] = -Bb[kk * kTBs + m0[t]];
 #pragma unroll
         for (int t = 0; t < NTL; ++t) bf[t] = Xq[kk * kTLd + t * 8];
 #pragma unroll
@@ -604,17 +942,18 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
           for (int nt = 0; nt < NTL; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
       }
       if (q == p - 1) {
-        // T_p complete: publish it as an MMA operand for the V_p product (visible after the next barrier)
+        // T_p complete: publish it as an MMA operand for the V_p product (visible after the next barrier) in the
+        // slot of A_p, which every warp has already moved into its accumulators (own tile positions only)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
           for (int nt = 0; nt < NTL; ++nt)
-            *reinterpret_cast<double2 *>(Ts + (size_t)(wm * 16 + mt * 8 + fr) * kTLd + wn * WR + nt * 8 + fk * 2) =
+            *reinterpret_cast<double2 *>(Xs + (size_t)(p * kDP + m0[mt] + fr) * kTLd + wn * WR + nt * 8 + fk * 2) =
                 make_double2(acc[mt][nt][0], acc[mt][nt][1]);
       }
     } else {
-      // X_p = V_p T_p  (m = column n' of panel p, k = column of T_p, n = row); for p = 0, T_0 = A_0 sits in Xs
-      const double *Tq = (p == 0 ? Xs : Ts) + wn * WR + fr;
+      // X_p = V_p T_p  (m = column n' of panel p, k = column of T_p, n = row); T_p (T_0 = A_0) sits in slot p of Xs
+      const double *Tq = Xs + (size_t)(p * kDP) * kTLd + wn * WR + fr;
       double x[2][NTL][2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt)
@@ -623,21 +962,22 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
 #pragma unroll
       for (int ks = 0; ks < kDP / 4; ++ks) {
         const int kk = ks * 4 + fk;
-        double af[2], bf[NTL];
-#pragma unroll
-        for (int t = 0; t < 2; ++t) af[t] = Bb[kk * kTBs + t * 8];
+        double bf[NTL];
 #pragma unroll
         for (int t = 0; t < NTL; ++t) bf[t] = Tq[kk * kTLd + t * 8];
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt)
+        for (int mt = 0; mt < 2; ++mt) {
+          if (ks * 4 >= m0[mt] + 8) continue;              // V_p[m][k] = 0 for k > m (warp-uniform)
+          const double af = Bb[kk * kTBs + m0[mt]];
 #pragma unroll
-          for (int nt = 0; nt < NTL; ++nt) dmma_m8n8k4(x[mt][nt][0], x[mt][nt][1], af[mt], bf[nt]);
+          for (int nt = 0; nt < NTL; ++nt) dmma_m8n8k4(x[mt][nt][0], x[mt][nt][1], af, bf[nt]);
+        }
       }
-      if (p == 0) __syncthreads();                         // everyone has read A_0 before it is overwritten by X_0
+      __syncthreads();                                     // everyone has read T_p before it is overwritten by X_p
       double *Y = ybuf + ((size_t)cell * kMaxWindow + p) * kDP * ldy;
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        const int col = wm * 16 + mt * 8 + fr;             // column inside panel p
+        const int col = m0[mt] + fr;                       // column inside panel p
         const double di = dinv[p * kDP + col];
 #pragma unroll
         for (int nt = 0; nt < NTL; ++nt) {

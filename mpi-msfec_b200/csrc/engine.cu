@@ -794,6 +794,8 @@ class Engine {
       CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<32>(kMaxWindow)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
       if (const char *b = std::getenv("MSFEC_DIRECT_TRSM_ROWS")) trsm_rows_ = std::atoi(b) == 32 ? 32 : 64;
+      if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_REGION")) fused_region_ = std::max(0, std::min(2, std::atoi(b)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow)));
       if (const char *b = std::getenv("MSFEC_DIRECT_LANES")) kDirectLanes = std::max(1, std::min(kMaxDirectLanes, std::atoi(b)));
       {
         // MSFEC_DIRECT_PRIO=1: descending stream priorities (lane 0 highest), so the later lanes fill the gaps
@@ -899,6 +901,8 @@ class Engine {
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
       *d_dp_rhs_ = nullptr, *d_dp_code_ = nullptr;
   bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
+  int fused_region_ = 2;                     // diagonal region of a chunk in one launch: MSFEC_DIRECT_FUSED_REGION = 0 (per-panel
+                                             // launches) | 1 (one warp per cell, FMA) | 2 (one warp per cell, DMMA block products)
   int trsm_rows_ = 32;                       // rows per CTA of k_direct_trsm (MSFEC_DIRECT_TRSM_ROWS = 32 | 64)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
   // sub-batches can be processed round-robin on several streams ("lanes") with private band storage; measured on
@@ -1156,6 +1160,21 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       for (int c0 = 0; c0 < n_panels; c0 += chunk) {
         const int c1 = std::min(n_panels, c0 + chunk), np = c1 - c0;
         const int row_hi = c1 * kDP;
+        if (fused_region_) {
+          // one warp per cell factors the whole diagonal region of the chunk
+          if (fused_region_ == 2)
+            k_direct_region_mma<<<nc, 32, region_mma_smem(np), stream_>>>(
+                d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
+          else
+            k_direct_region<<<(nc + kRegionWarps - 1) / kRegionWarps, 32 * kRegionWarps, 0, stream_>>>(
+                d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, nc, d_dvec_, d_vinv_, d_flag_ + 2);
+          ++launches_;
+          for (int j = c0 + 1; j < c1; ++j) {               // same algorithmic flops as the strip updates below
+            const double R = row_hi - j * kDP, Cn = kDP;
+            direct_flops_ += 2.0 * kDP * (j - c0) * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
+          }
+          mark("region");
+        } else
         for (int j = c0; j < c1; ++j) {
           const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
           if (j > c0) launch_update(s, c0 * kDP, j - c0, j0, j0 + kDP, true, row_hi);
