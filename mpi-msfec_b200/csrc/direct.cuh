@@ -64,7 +64,7 @@ __global__ void k_direct_fill_rhs(int NI, int k, const int *__restrict__ rhs_des
 
 // Fused zero + fill: every band entry is written exactly once (value or 0) with 16-byte stores, driven by
 // a per-entry code table shared by all cells (0: zero, 1: per-cell slot reference, 2: cell-independent value
-// x kscale, 3: constant, 4: right-hand side (row, j)).  Replaces memset + the four scatter kernels above
+// x kscale, 3: constant, 4: right-hand side (row, j), 7: never read, not written).  Replaces memset + the four scatter kernels above
 // (whose 8-byte scattered writes cost a read-modify-write per sector).
 // grid (ceil(n_entries / 512), ceil(cells / 4)), block 256; band entries in pairs
 __device__ __forceinline__ double fill_value(int code, const double *__restrict__ vals_cell, const double *__restrict__ sval,
@@ -86,6 +86,7 @@ k_direct_fill_fused(const int2 *__restrict__ code, long long n_pairs, const doub
   const long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (e >= n_pairs) return;
   const int2 c = code[e];
+  if (c.x == 7 && c.y == 7) return;                        // never-read upper block: leave unwritten
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int ci = blockIdx.y * 4 + u;
@@ -1161,16 +1162,32 @@ k_direct_back_diag(const double *__restrict__ band, size_t band_stride, DirectPl
   }
 }
 
-// xT[cell][j][p] -> interleaved x[g][row][k][32].  grid (ceil(NP/256), cells), block 256
-__global__ void k_direct_scatter_x(int NP, int NI, int k, const int *__restrict__ inv_perm, const double *__restrict__ xT,
-                                   int cell_lo, double *__restrict__ x) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= NP) return;
-  const int row = inv_perm[p];
-  const int cell = cell_lo + blockIdx.y, g = cell / kLanes, lane = cell % kLanes;
-  if (row < 0) return;
-  for (int j = 0; j < k; ++j)
-    x[(((size_t)g * NI + row) * k + j) * kLanes + lane] = xT[((size_t)blockIdx.y * k + j) * NP + p];
+// xT[cell][j][p] -> interleaved x[g][row][k][32]: a CTA transposes 32 cells x 32 padded indices per right-hand side
+// through shared memory, so both the per-cell reads and the cell-interleaved writes are 256-byte coalesced (the
+// one-thread-per-entry version wrote 8 bytes per 256-byte line).  cell_lo is a multiple of 32.
+// grid (NP/32, ceil(cells/32)), block (32, 8)
+__global__ void __launch_bounds__(256)
+k_direct_scatter_x(int NP, int NI, int k, const int *__restrict__ inv_perm, const double *__restrict__ xT,
+                   int cell_lo, int n_cells, double *__restrict__ x) {
+  __shared__ double tile[kLanes][kDP + 1];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const int p0 = blockIdx.x * kDP, c0 = blockIdx.y * kLanes;
+  const int g = (cell_lo + c0) / kLanes;
+  int rows[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) rows[t] = inv_perm[p0 + w + 8 * t];
+  for (int j = 0; j < k; ++j) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = w + 8 * t;                              // cell inside the group
+      tile[c][lane] = (c0 + c < n_cells) ? xT[((size_t)(c0 + c) * k + j) * NP + p0 + lane] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+      if (rows[t] >= 0) x[(((size_t)g * NI + rows[t]) * k + j) * kLanes + lane] = tile[lane][w + 8 * t];
+    __syncthreads();
+  }
 }
 
 // rows whose solution is fixed to zero (RT_DQ pinned DoF) -- the interleaved x buffer is cleared first.

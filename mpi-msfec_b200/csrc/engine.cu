@@ -784,6 +784,17 @@ class Engine {
         for (int r = 0; r < T_.NI; ++r)
           if (P_.rhs_dest[r] >= 0)
             for (int j = 0; j < T_.k_solve; ++j) code[P_.rhs_dest[r] + j] = ((r * 32 + j) << 3) | 4;
+        if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_REGION")) fused_region_ = std::max(0, std::min(2, std::atoi(b)));
+        if (fused_region_) {
+          // 32x32 blocks strictly above the diagonal of a block column's own block are never read by the fused-region
+          // schedule (lower-triangular factorisation): code 7 = leave unwritten (15 % of the band for Ned_RT, n = 8)
+          for (int sb = 0; sb < P_.n_slabs; ++sb)
+            for (int c = 0; c < P_.bs[sb]; ++c)
+              for (int r = 0; r < (c / kDP) * kDP; ++r) {
+                int32_t &cd = code[(size_t)P_.col_off[sb] + (size_t)c * P_.ld[sb] + r];
+                if (cd == 0) cd = 7;
+              }
+        }
         d_dp_code_ = dev_upload(code);
       }
       for (int v : P_.ld) ldy_ = std::max(ldy_, v);
@@ -1215,7 +1226,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       }
     }
     mark("backward");
-    k_direct_scatter_x<<<dim3((NP + 255) / 256, nc), 256, 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, d_vec_[7]);
+    k_direct_scatter_x<<<dim3(NP / kDP, (nc + kLanes - 1) / kLanes), dim3(kLanes, 8), 0, stream_>>>(NP, NI, k, d_dp_inv_, d_xT_, lo, nc, d_vec_[7]);
     mark("scatter");
     ++launches_;
     if (timed) {

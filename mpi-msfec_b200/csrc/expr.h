@@ -47,7 +47,12 @@ MSFEC_HD double expr_eval(const ExprInstr *prog, int len, double x, double y, do
       case OP_SUB: --sp; st[sp - 1] = st[sp - 1] - st[sp]; break;
       case OP_MUL: --sp; st[sp - 1] = st[sp - 1] * st[sp]; break;
       case OP_DIV: --sp; st[sp - 1] = st[sp - 1] / st[sp]; break;
-      case OP_POW: --sp; st[sp - 1] = pow(st[sp - 1], st[sp]); break;
+      case OP_POW: {   // small integer exponents (x^2, x^3 in the reference's .prm right-hand sides) as products
+        --sp;
+        const double b = st[sp - 1], e = st[sp];
+        st[sp - 1] = e == 2.0 ? b * b : (e == 3.0 ? b * b * b : (e == 1.0 ? b : pow(b, e)));
+        break;
+      }
       case OP_MIN: --sp; st[sp - 1] = fmin(st[sp - 1], st[sp]); break;
       case OP_MAX: --sp; st[sp - 1] = fmax(st[sp - 1], st[sp]); break;
       case OP_NEG: st[sp - 1] = -st[sp - 1]; break;
