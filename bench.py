@@ -153,7 +153,16 @@ def cpu_oracle_throughput(n_sample, g_ref, L, cores):
     return per * cores / dt, per * cores, dt
 
 
+def _emit(line, fd):
+    """The ONE JSON line goes to the process' original stdout; everything else that writes to fd 1 during the run
+    (NCCL prints its version banner there) was redirected to stderr."""
+    os.write(fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    sys.stdout.flush()
+    out_fd = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -204,7 +213,7 @@ def main():
                                            f"(exact SuperLU solve per cell), {cores} processes"},
                 "e2e": {"value": v, "unit": "coarse cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "fine_dof_solves_per_s": v * k * (n_fine or 0)}
-        print(json.dumps(line))
+        _emit(line, out_fd)
         return
 
     # ---------------- B200 arm ------------------------------------------------------------------
@@ -336,7 +345,7 @@ def main():
             line["cpu_baseline"] = {"value": v, "unit": "coarse cells/s", "cores": cores, "kind": "port",
                                     "sample": f"{n_done} cells of the same workload in {dt:.1f} s, "
                                               f"oracle/msfec_oracle.py (exact SuperLU solve per cell), {cores} processes"}
-        print(json.dumps(line))
+        _emit(line, out_fd)
     if world > 1:
         dist.destroy_process_group()
 

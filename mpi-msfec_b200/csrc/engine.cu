@@ -1119,7 +1119,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     const int ne = (int)P_.cell_dest.size(), nes = (int)P_.shared_dest.size(), nek = (int)P_.const_dest.size();
     if (fused_fill_) {
       const long long n_pairs = (long long)(stride / 2);
-      k_direct_fill_fused<<<dim3((unsigned)((n_pairs + 255) / 256), (nc + 3) / 4), 256, 0, stream_>>>(
+      k_direct_fill_fused<<<dim3((unsigned)((n_pairs + 255) / 256), (nc + kFillCells - 1) / kFillCells), 256, 0, stream_>>>(
           (const int2 *)d_dp_code_, n_pairs, d_vals_, n_slots_, d_dp_sval_, kscale, d_dp_kval_, d_vec_[2], NI, k, lo, nc, d_band_, stride);
       launches_ -= 3;
     } else {
