@@ -28,6 +28,100 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 }  // namespace msfec
 #include "../mpi-msfec_b200/csrc/direct.cuh"
 
+namespace msfec {
+namespace {
+// EXPERIMENT (not shipped): measured 18.3 / 20.2 / 20.7 TFLOP/s at K = 96 / 160 / 192 against 27.1 / 28.3 / 28.6 for the
+// shared-memory ring of k_direct_update_s -- 8 poorly coalesced fragment loads per 16 DMMAs bind the LSU.
+// ---- trailing update, warp-private version ---------------------------------------------------
+// Same operation and tile enumeration as k_direct_update_s<64,64>, but every warp feeds its 32x32 DMMA tile straight
+// from global memory (L1/L2) into MMA fragments: no shared memory, no block-wide barriers, no cp.async ring.  A fragment
+// load of a warp touches 4 k-rows x 64 contiguous bytes (full sectors); the two warps of a CTA that share an operand
+// hit in L1.  The next k-step's 8 fragment values are prefetched into registers while the current 16 DMMAs issue.
+// grid (tiles, cells), block 128
+__global__ void __launch_bounds__(128, 4)
+k_direct_update_w(double *__restrict__ band, size_t band_stride, DirectPlanDev D, int s, int jsrc, int nq, int yslot0,
+                  int vc_lo, int vc_hi, const double *__restrict__ ybuf, int ldy) {
+  constexpr int TM = 64, TN = 64;
+  const int cell = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ld = D.ld[s], front_rows = D.front_rows[s];
+  int cbase = vc_lo, rbase;
+  {
+    int t = blockIdx.x;
+    for (;; cbase += TN) {
+      const int r_first = cbase - (cbase - vc_lo) % TM;
+      const int T = (ld - r_first + TM - 1) / TM;
+      if (t < T) { rbase = r_first + t * TM; break; }
+      t -= T;
+    }
+  }
+  const int wr = warp >> 1, wc = warp & 1;
+  const int fr = lane >> 2, fk = lane & 3;
+  const int vc0 = cbase + wc * 32, vr0 = rbase + wr * 32;
+  if (!(vc0 < vc_hi && vc0 < front_rows && vr0 >= vc0 && vr0 < ld)) return;     // warp-uniform
+  const bool diagw = vr0 == vc0;
+  const long long col_off = D.col_off[s];
+  const int choff = D.chunk_off[s];
+  double *cb = band + (size_t)cell * band_stride;
+  const double *Lp = cb + col_off + (size_t)jsrc * ld + (size_t)fk * ld + vr0 + fr;                      // B[k][n = row]
+  const double *Yp = ybuf + ((size_t)cell * kMaxWindow + yslot0) * kDP * ldy + (size_t)fk * ldy + vc0 + fr;   // A[m = col][k]
+  double *cdst;
+  int ldc = ld;
+  {
+    const int cblk = D.chunk_blk[choff + (vc0 >> 5)];
+    int roff = vr0;
+    if (cblk == s) cdst = cb + col_off + (size_t)vc0 * ld;
+    else {
+      ldc = D.ld[cblk];
+      cdst = cb + D.col_off[cblk] + (size_t)D.chunk_local[choff + (vc0 >> 5)] * ldc;
+      const int rb = D.chunk_blk[choff + (vr0 >> 5)];
+      roff = rb < 0 ? D.front_rows[cblk] + (vr0 - front_rows)
+                    : D.front_pos[cblk * D.n_slabs + rb] + D.chunk_local[choff + (vr0 >> 5)];
+    }
+    cdst += (size_t)fr * ldc + roff + fk * 2;
+  }
+  const int nk = nq * (kDP / 4);
+  double af[4], bf[4], an[4], bn[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) { af[t] = Yp[t * 8]; bf[t] = Lp[t * 8]; }
+  double acc[4][4][2];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const double2 v = *reinterpret_cast<const double2 *>(cdst + (size_t)(mt * 8) * ldc + nt * 8);
+      acc[mt][nt][0] = v.x; acc[mt][nt][1] = v.y;
+    }
+  for (int ks = 0; ks < nk; ++ks) {
+    if (ks + 1 < nk) {
+      const double *yp = Yp + (size_t)(ks + 1) * 4 * ldy, *lp = Lp + (size_t)(ks + 1) * 4 * ld;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { an[t] = yp[t * 8]; bn[t] = lp[t * 8]; }
+    }
+    if (diagw) {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = mt; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    } else {
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+    }
+#pragma unroll
+    for (int t = 0; t < 4; ++t) { af[t] = an[t]; bf[t] = bn[t]; }
+  }
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+      *reinterpret_cast<double2 *>(cdst + (size_t)(mt * 8) * ldc + nt * 8) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+}
+
+
+}  // namespace
+}  // namespace msfec
+
 using namespace msfec;
 
 template <typename T> T *upload(const std::vector<T> &v) {
@@ -115,6 +209,14 @@ int main(int argc, char **argv) {
       k_direct_update_s<TM, TN, KC, ST, MB><<<dim3(update_s_tiles<TM, TN>(576, vc_lo, 544), cells), (TM / 32) * (TN / 32) * 32, update_s_smem<TM, TN, KC, ST>()>>>( \
           band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, ybuf, ldy);                                                  \
     });                                                                                                                \
+  }
+#define WARP(nq, vc_lo)                                                                                                \
+  run("warp-private (no smem)", nq, vc_lo, [&] {                                                                        \
+    k_direct_update_w<<<dim3(update_s_tiles<64, 64>(576, vc_lo, 544), cells), 128>>>(band, band_doubles, D, 0, 0, nq, 0, vc_lo, 544, ybuf, ldy); \
+  });
+  for (int nq : {3, 5, 6}) {
+    NEW(64, 64, 8, 4, 4, nq, 192)
+    WARP(nq, 192)
   }
   for (int nq : {3, 4, 6}) {
     if (nq <= 4) OLD(64, 64, nq, 192)
