@@ -78,7 +78,7 @@ __device__ __forceinline__ double fill_value(int code, const double *__restrict_
   return b_cell[((size_t)(a >> 5) * k + (a & 31)) * kLanes];
 }
 
-constexpr int kFillCells = 16;   // cells per CTA: the code table is read once per 16 cells
+constexpr int kFillCells = 4;    // cells per CTA (16 cells per CTA with a zero fast path measured 8.78 vs 8.59 ms per 4096 cells)
 __global__ void __launch_bounds__(256)
 k_direct_fill_fused(const int2 *__restrict__ code, long long n_pairs, const double *__restrict__ vals, int n_slots,
                     const double *__restrict__ sval, double kscale, const double *__restrict__ kval,
@@ -88,24 +88,18 @@ k_direct_fill_fused(const int2 *__restrict__ code, long long n_pairs, const doub
   if (e >= n_pairs) return;
   const int2 c = code[e];
   if (c.x == 7 && c.y == 7) return;                        // never-read upper block: leave unwritten
-  const int ci0 = blockIdx.y * kFillCells;
-  if (!(c.x | c.y)) {
-    // 94 % of the band: plain zeros, kFillCells independent 16-byte stores per thread
 #pragma unroll
-    for (int u = 0; u < kFillCells; ++u)
-      if (ci0 + u < n_cells) *reinterpret_cast<double2 *>(band + (size_t)(ci0 + u) * band_stride + 2 * e) = make_double2(0.0, 0.0);
-    return;
-  }
-#pragma unroll 4
   for (int u = 0; u < kFillCells; ++u) {
-    const int ci = ci0 + u;
+    const int ci = blockIdx.y * kFillCells + u;
     if (ci >= n_cells) break;
-    const int cell = cell_lo + ci, g = cell / kLanes, lane = cell % kLanes;
-    const double *vc = vals + (size_t)g * n_slots * kLanes + lane;
-    const double *bc = b + (size_t)g * NI * k * kLanes + lane;
-    double2 v;
-    v.x = fill_value(c.x, vc, sval, kscale, kval, bc, k);
-    v.y = fill_value(c.y, vc, sval, kscale, kval, bc, k);
+    double2 v = make_double2(0.0, 0.0);
+    if (c.x | c.y) {
+      const int cell = cell_lo + ci, g = cell / kLanes, lane = cell % kLanes;
+      const double *vc = vals + (size_t)g * n_slots * kLanes + lane;
+      const double *bc = b + (size_t)g * NI * k * kLanes + lane;
+      v.x = fill_value(c.x, vc, sval, kscale, kval, bc, k);
+      v.y = fill_value(c.y, vc, sval, kscale, kval, bc, k);
+    }
     *reinterpret_cast<double2 *>(band + (size_t)ci * band_stride + 2 * e) = v;
   }
 }

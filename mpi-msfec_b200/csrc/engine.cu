@@ -1343,7 +1343,16 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     k_apply_full<<<dim3((T_.NF + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(full_.dev, T_.NF, T_.blk[0].n_total, T_.k0, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
     const int rhs_off = T_.rhs_block ? T_.blk[0].n_total : 0;
     {
-      const int n_slices = std::max(1, std::min(16, (2 * 148 + groups - 1) / groups));
+      // d-slices per group: the count <= 16 that fills whole waves of 2 CTAs/SM best (3 slices x 128 groups = 384 CTAs
+      // on 296 slots ran 1.3 waves at 65 % utilisation)
+      int n_slices = 1;
+      {
+        double best = 0.0;
+        for (int n = 1; n <= 16; ++n) {
+          const double ctas = (double)n * groups, util = ctas / (std::ceil(ctas / 296.0) * 296.0);
+          if (util > best + 1e-9) { best = util; n_slices = n; }
+        }
+      }
       const size_t need = (size_t)n_slices * groups * kLanes * (kGramJ * kGramJ + kGramJ);
       if (need > gram_part_size_) {
         cudaFree(d_gram_part_);
