@@ -205,16 +205,32 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
     ctx->topo = build_topology(p->pairing, 1 << p->n_refine_local);
     make_spec(*p, ctx->topo, ctx->spec);
     {
-      // RT_DQ: a layer block alone is a pure-Neumann sub-problem (singular pivot); keep layer + plane together
+      // RT_DQ: a layer block alone is a pure-Neumann sub-problem (singular pivot); keep layer + plane together.
+      // Otherwise: layers/planes, or nested dissection when its symbolic flop count is lower (from n = 16 on).
       int ordering = p->pairing == MSFEC_RT_DQ ? 1 : 0;
-      if (const char *e = std::getenv("MSFEC_DIRECT_ORDERING")) ordering = std::string(e) == "slab" ? 1 : ordering;
-      try {
-        ctx->plan = build_direct_plan(ctx->topo, ordering);
-      } catch (const std::exception &) {
-        // only fatal if the direct path is requested (e.g. band > 2^31 entries per cell at 5+ local refinements)
-        if (p->use_direct_solver_basis) throw;
-        ctx->plan = DirectPlan();
+      bool forced = false;
+      if (const char *e = std::getenv("MSFEC_DIRECT_ORDERING")) {
+        const std::string v = e;
+        if (v == "slab") { ordering = 1; forced = true; }
+        else if (v == "split" && p->pairing != MSFEC_RT_DQ) { ordering = 0; forced = true; }
+        else if (v == "nd" && p->pairing != MSFEC_RT_DQ) { ordering = 2; forced = true; }
       }
+      std::string why;
+      auto try_plan = [&](int ord, DirectPlan &out) {
+        try { out = build_direct_plan(ctx->topo, ord); return true; }
+        catch (const std::exception &ex) { why = ex.what(); return false; }
+      };
+      DirectPlan plan;
+      bool have = try_plan(ordering, plan);
+      // nested dissection only where the factorisation is flop-bound (>= 5 GFLOP per cell) and it saves >= 15 %: its many
+      // small blocks mean more (and smaller) launches (C1, Q at n = 16: 0.6 GFLOP, 6.8 ms with layers/planes, 9.9 ms with ND)
+      if (!forced && p->pairing != MSFEC_RT_DQ && ((have && plan.update_flops >= 5e9) || !have)) {
+        DirectPlan nd;
+        if (try_plan(2, nd) && (!have || nd.update_flops < 0.85 * plan.update_flops)) { plan = std::move(nd); have = true; }
+      }
+      // a missing plan is only fatal if the direct path is requested (band > 2^31 entries per cell at 5+ local refinements)
+      if (!have && p->use_direct_solver_basis) throw std::runtime_error(why);
+      ctx->plan = have ? std::move(plan) : DirectPlan();
     }
     if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan);
     *out = ctx;
@@ -347,6 +363,8 @@ int msfec_debug_table(const msfec_ctx *ctx, const char *name, void *out, size_t 
       else if (n == pre + ".val") dv = &nops[i].val;
     }
   }
+  std::vector<double> plan_info;
+  if (n == "direct.info") { plan_info = {dp.update_flops, (double)dp.band_doubles, (double)dp.n_slabs, (double)dp.NP}; dv = &plan_info; }
   if (n == "G") dv = &t.G; else if (n == "F1") dv = &t.F1;
   else if (n == "diag_slot0") iv = &t.diag_slot0; else if (n == "diag_slot1") iv = &t.diag_slot1;
   else if (n == "blk0.cell_dofs") iv = &t.blk[0].cell_dofs; else if (n == "blk1.cell_dofs") iv = &t.blk[1].cell_dofs;

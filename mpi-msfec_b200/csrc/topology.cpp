@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <functional>
 #include <map>
 #include <stdexcept>
 
@@ -544,16 +546,64 @@ DirectPlan build_direct_plan(const Topology &t, int ordering) {
     const int kz = (int)std::floor(z);
     return on_plane ? 2 * kz - 1 : 2 * kz;
   };
-  std::map<int, std::vector<int>> by_key;   // stacked interior row indices, sigma-type first
-  for (int d = 0; d < NI0; ++d) by_key[key_of(0, d)].push_back(d);
-  for (int d = 0; d < NI1; ++d) by_key[key_of(1, d)].push_back(NI0 + d);
   std::vector<std::vector<int>> slabs;
-  for (auto &kv : by_key) slabs.push_back(kv.second);
+  if (ordering == 2) {
+    // Geometric nested dissection (doubled integer coordinates 0..2n): a box with more than kMinCells fine cells along
+    // its longest axis is cut by the mesh plane through its middle; the two halves are eliminated first (recursively),
+    // then the DoFs ON the cut as one block.  Every leading set of blocks is again a union of sub-box problems with
+    // essential conditions on the cuts, so the no-pivot argument of the layer/plane ordering carries over (not for
+    // RT_DQ, where a box interior alone is a pure-Neumann problem).  The separator planes are NOT dissected further:
+    // for Ned_RT a leading set that contains a plane only up to a line of fixed edge DoFs is a box with a slit spanning
+    // two faces, which is not simply connected -- the Schur complement K A00^-1 K^T + A11 of that sub-problem has a
+    // kernel and the pivots change sign (measured) -- and for Q_Ned the many small separator pieces cost more 32-padding
+    // than the fill they save (n = 16: 689 instead of 549 panels for the same 23.8 GFLOP).  Pays off from n = 16
+    // (Ned_RT: 35 instead of 51 GFLOP per cell, Q_Ned 24 instead of 34); at n = 8 the padding of the small blocks
+    // costs more than the fill it saves (profiles/ordering_model.py).
+    constexpr int kMinCells = 4;
+    struct Dof { int row; int p[3]; };
+    std::vector<Dof> all;
+    for (int b = 0; b < (t.two_blocks ? 2 : 1); ++b) {
+      const int ni = b == 0 ? NI0 : NI1;
+      for (int d = 0; d < ni; ++d) {
+        Dof q; q.row = (b == 0 ? 0 : NI0) + d;
+        for (int c = 0; c < 3; ++c) q.p[c] = (int)std::lround(2.0 * t.blk[b].pos[3 * d + c]);
+        all.push_back(q);
+      }
+    }
+    auto emit = [&](std::vector<int> &idx) {
+      if (idx.empty()) return;
+      std::vector<int> rows;
+      for (int i : idx) rows.push_back(all[i].row);
+      std::sort(rows.begin(), rows.end());               // stacked numbering: sigma-type rows first
+      slabs.push_back(rows);
+    };
+    std::function<void(int[3], int[3], std::vector<int> &)> rec = [&](int lo[3], int hi[3], std::vector<int> &idx) {
+      int d = -1, best = kMinCells;
+      for (int a : {2, 1, 0}) if ((hi[a] - lo[a]) / 2 > best) { best = (hi[a] - lo[a]) / 2; d = a; }
+      if (d < 0 || (int)idx.size() <= PW) { emit(idx); return; }
+      const int mid = lo[d] + ((hi[d] - lo[d]) / 4) * 2;
+      std::vector<int> L, R, Sp;
+      for (int i : idx) (all[i].p[d] < mid ? L : all[i].p[d] > mid ? R : Sp).push_back(i);
+      int l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
+      h2[d] = mid; rec(l2, h2, L);
+      h2[d] = hi[d]; l2[d] = mid; rec(l2, h2, R);
+      emit(Sp);
+    };
+    std::vector<int> idx(all.size());
+    for (size_t i = 0; i < all.size(); ++i) idx[i] = (int)i;
+    int lo[3] = {0, 0, 0}, hi[3] = {2 * n, 2 * n, 2 * n};
+    rec(lo, hi, idx);
+  } else {
+    std::map<int, std::vector<int>> by_key;   // stacked interior row indices, sigma-type first
+    for (int d = 0; d < NI0; ++d) by_key[key_of(0, d)].push_back(d);
+    for (int d = 0; d < NI1; ++d) by_key[key_of(1, d)].push_back(NI0 + d);
+    for (auto &kv : by_key) slabs.push_back(kv.second);
+  }
   // Padding-aware balancing: a block whose size exceeds a multiple of 32 by a few DoFs hands its last
   // u-type DoFs to the next block if they fit into that block's padding (n = 8 Ned_RT: layers 161 -> 160).
   // Deferring u-type DoFs keeps every leading matrix non-singular (the leading Schur complement only loses
   // rows/columns), so the no-pivot factorisation is unaffected.
-  for (size_t s = 0; s + 1 < slabs.size(); ++s) {
+  for (size_t s = 0; ordering != 2 && s + 1 < slabs.size(); ++s) {
     const int excess = (int)slabs[s].size() % PW;
     const int next_fill = (int)slabs[s + 1].size() % PW;
     int n_u = 0;

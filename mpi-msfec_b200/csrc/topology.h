@@ -130,7 +130,8 @@ std::vector<NormOperator> build_norm_operators(const Topology &t);
 
 // Builds everything above.  pairing: enum msfec_pairing; n = 2^L.
 Topology build_topology(int pairing, int n);
-// ordering: 0 = split layers/planes (default), 1 = slabs
+// ordering: 0 = split layers/planes (default), 1 = slabs, 2 = geometric nested dissection (chosen automatically from
+// n = 16 on when its symbolic update flop count is lower; MSFEC_DIRECT_ORDERING = split | slab | nd overrides)
 DirectPlan build_direct_plan(const Topology &t, int ordering = 0);
 
 // Quadrature abscissae of QGauss<3>(2) on the unit cube, x fastest.

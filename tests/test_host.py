@@ -181,3 +181,30 @@ def test_norm_operator_tables_match_oracle_gram_matrices(msfec, pairing):
         Go = sp.csr_matrix(ref[name])[p][:, p]
         assert abs(G - Go).max() <= 1e-13 * abs(Go).max(), (pairing, name)
         assert abs(G - G.T).max() == 0.0
+
+
+def test_direct_plan_nested_dissection(msfec, monkeypatch):
+    """The nested-dissection block ordering (chosen automatically at 4 local refinements for Q_Ned / Ned_RT, forced here at
+    3): the no-pivot LDL^T in the library's padded order reproduces the sparse-LU solution, pivots keep their signs
+    (positive on sigma-type, negative on u-type unknowns), and the symbolic structure differs from layers/planes."""
+    monkeypatch.setenv("MSFEC_DIRECT_ORDERING", "nd")
+    pairing, L, seed = "NED_RT", 3, 20261017
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
+    info = bb.table("direct.info")
+    assert int(info[2]) == 15 and int(info[3]) == 2688          # 8 boxes of 4^3 fine cells + 4 + 2 + 1 separator planes
+    cells = mo.morton_cells(2)
+    prob = oracle_problem(pairing, L, random_seed=seed)
+    M, r, Z, dbg = emulate.emulate_cell(bb, prob, cells[37], 37)
+    D = emulate.dims_of(bb)
+    h = (cells[37][7][0] - cells[37][0][0]) / D["n"]
+    x, d, inv = emulate.emulate_direct(bb, dbg["vals"], h ** D["k_h_exponent"], dbg["b"])
+    ref = dbg["x"]
+    assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+    real = inv >= 0
+    is_u = np.zeros(len(inv), bool); is_u[real] = inv[real] >= D["NI0"]
+    assert (d[real & ~is_u] > 0).all() and (d[real & is_u] < 0).all()
+    monkeypatch.delenv("MSFEC_DIRECT_ORDERING")
+    bb2 = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
+    assert int(bb2.table("direct.info")[3]) == 2656              # layers/planes stay the default at n = 8
+    bb4 = msfec.BasisBuilder(lib_problem(msfec, pairing, 4), device=-1)
+    assert int(bb4.table("direct.info")[2]) == 127               # nested dissection chosen at n = 16
