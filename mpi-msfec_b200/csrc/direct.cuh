@@ -851,19 +851,20 @@ k_direct_update_s(double *__restrict__ band, size_t band_stride, DirectPlanDev D
 // grid ((ld - row_lo) / 32, cells), block 128 (warp = 16 columns x 16 rows of the current panel)
 constexpr int kTBs = kDP + 4;
 template <int TR>
-constexpr size_t trsm_smem_bytes(int np) {
+constexpr size_t trsm_smem_bytes(int np) {   // independent of the warp count
   return ((size_t)np * kDP * (TR + 4) + 3 * kDP * kTBs + (size_t)np * kDP) * sizeof(double);
 }
 
-// TR rows per CTA (32 or 64): a warp owns 16 columns x TR/2 rows of the current panel.  TR = 64 halves the number
-// of times the 32x32 operand blocks are re-streamed from L2 and doubles the independent MMAs per fragment load;
-// the last CTA of a launch may own only 32 valid rows (row counts are multiples of 32).
-template <int TR>
-__global__ void __launch_bounds__(128)
+// TR rows per CTA (32 or 64), NW warps (4 or 8): a warp owns two 8-column tiles x TR / (NW/2) rows of the current panel.
+// TR = 64 halves the number of times the 32x32 operand blocks are re-streamed from L2; with 4 warps it doubles the
+// independent MMAs per fragment load, with 8 warps it keeps 16-row warp tiles and 16 warps/SM at 2 CTAs/SM.
+// The last CTA of a launch may own only 32 valid rows (row counts are multiples of 32).
+template <int TR, int NW>
+__global__ void __launch_bounds__(32 * NW)
 k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int jc0, int np, int row_lo,
               int pglob0, int NP, const double *__restrict__ vinv, const double *__restrict__ dvec,
               double *__restrict__ ybuf, int ldy) {
-  constexpr int kTLd = TR + 4, NTL = TR / 16, WR = TR / 2;   // smem row stride, n-tiles and rows per warp
+  constexpr int NT = 32 * NW, kTLd = TR + 4, WR = TR / (NW / 2), NTL = WR / 8;   // threads, smem row stride, rows and n-tiles per warp
   extern __shared__ __align__(16) double trsm_smem[];
   double *Xs = trsm_smem;                                  // [32 np][kTLd]   A, then X
   double *Bs = Xs + (size_t)np * kDP * kTLd;               // [3][32][kTBs]   operand ring, [k][n]
@@ -873,14 +874,14 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
   double *P = band + (size_t)cell * band_stride + col_off;
   const int W = np * kDP;
   // stage the A tile: W columns x TR rows = TR/2 chunks of 16 bytes per column
-  for (int c = tid; c < W * (TR / 2); c += 128) {
+  for (int c = tid; c < W * (TR / 2); c += NT) {
     const int k = c / (TR / 2), i = (c % (TR / 2)) * 2;
     double *d = Xs + k * kTLd + i;
     if (r0 + i < ld) cp_async16(d, P + (size_t)(jc0 + k) * ld + r0 + i);
     else { d[0] = 0.0; d[1] = 0.0; }
   }
   cp_async_commit();
-  for (int c = tid; c < W; c += 128) dinv[c] = 1.0 / dvec[(size_t)cell * NP + pglob0 + c];
+  for (int c = tid; c < W; c += NT) dinv[c] = 1.0 / dvec[(size_t)cell * NP + pglob0 + c];
   const int nblk = np * (np + 1) / 2;
   // block sequence: for p: L(p,0) .. L(p,p-1), V_p
   auto stage_blk = [&](int b, int p, int q) {
@@ -890,8 +891,8 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
     if (q < p) { src = P + (size_t)(jc0 + q * kDP) * ld + jc0 + p * kDP; lds = ld; }
     else { src = vinv + ((size_t)cell * NP + pglob0 + p * kDP) * kDP; lds = kDP; }
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      const int c = tid + t * 128;
+    for (int t = 0; t < 512 / NT; ++t) {
+      const int c = tid + t * NT;
       const int k = c >> 4, n = (c & 15) * 2;
       cp_async16(dst + k * kTBs + n, src + (size_t)k * lds + n);
     }
@@ -903,7 +904,7 @@ k_direct_trsm(double *__restrict__ band, size_t band_stride, long long col_off, 
     if (b < nblk) { stage_blk(b, sp, sq); advance(sp, sq); }
     cp_async_commit();
   }
-  const int wm = warp >> 1, wn = warp & 1;                 // wm: column tiles (MMA m), wn: row half (MMA n)
+  const int wm = warp / (NW / 2), wn = warp % (NW / 2);    // wm: column tiles (MMA m), wn: row slice (MMA n)
   const int fr = lane >> 2, fk = lane & 3;
   // a warp owns the 8-column tiles {wm, 3 - wm} of the panel: V_p is lower triangular, so tile t needs only the
   // k-steps below 8 (t + 1); pairing tile t with 3 - t gives both warps 10 of the 16 k-steps (5/8 of the MMAs)

@@ -802,9 +802,10 @@ class Engine {
       CUDA_OK(cudaFuncSetAttribute(k_direct_update_s<64, 64, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_s_smem<64, 64, 8, 4>()));
       if (const char *b = std::getenv("MSFEC_DIRECT_CHUNK")) direct_chunk_ = std::max(1, std::min(kMaxWindow, std::atoi(b)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_back_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackGemmSmem));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<32>(kMaxWindow)));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
-      if (const char *b = std::getenv("MSFEC_DIRECT_TRSM_ROWS")) trsm_rows_ = std::atoi(b) == 32 ? 32 : 64;
+      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<32>(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
+      if (const char *b = std::getenv("MSFEC_DIRECT_TRSM_ROWS")) { const int v = std::atoi(b); trsm_rows_ = v == 32 ? 32 : (v == 648 ? 648 : 64); }
       if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_REGION")) fused_region_ = std::max(0, std::min(2, std::atoi(b)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow)));
       if (const char *b = std::getenv("MSFEC_DIRECT_LANES")) kDirectLanes = std::max(1, std::min(kMaxDirectLanes, std::atoi(b)));
@@ -915,7 +916,7 @@ class Engine {
   bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
   int fused_region_ = 2;                     // diagonal region of a chunk in one launch: MSFEC_DIRECT_FUSED_REGION = 0 (per-panel
                                              // launches) | 1 (one warp per cell, FMA) | 2 (one warp per cell, DMMA block products)
-  int trsm_rows_ = 32;                       // rows per CTA of k_direct_trsm (MSFEC_DIRECT_TRSM_ROWS = 32 | 64)
+  int trsm_rows_ = 32;                       // k_direct_trsm tile: MSFEC_DIRECT_TRSM_ROWS = 32 (4 warps) | 64 (4 warps) | 648 (64 rows, 8 warps)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
   // sub-batches can be processed round-robin on several streams ("lanes") with private band storage; measured on
   // B200 this gains nothing (every large kernel fills the GPU and kernels of different streams effectively run
@@ -1201,11 +1202,14 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
             mark("panel");
           }
         }
-        if (trsm_rows_ == 64)
-          k_direct_trsm<64><<<dim3((ld - row_hi + 63) / 64, nc), 128, trsm_smem_bytes<64>(np), stream_>>>(
+        if (trsm_rows_ == 648)        // 64 rows, 8 warps
+          k_direct_trsm<64, 8><<<dim3((ld - row_hi + 63) / 64, nc), 256, trsm_smem_bytes<64>(np), stream_>>>(
+            d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+        else if (trsm_rows_ == 64)
+          k_direct_trsm<64, 4><<<dim3((ld - row_hi + 63) / 64, nc), 128, trsm_smem_bytes<64>(np), stream_>>>(
             d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
         else
-          k_direct_trsm<32><<<dim3((ld - row_hi) / 32, nc), 128, trsm_smem_bytes<32>(np), stream_>>>(
+          k_direct_trsm<32, 4><<<dim3((ld - row_hi) / 32, nc), 128, trsm_smem_bytes<32>(np), stream_>>>(
             d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
         ++launches_;
         mark("trsm");
