@@ -213,7 +213,7 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
         const std::string v = e;
         if (v == "slab") { ordering = 1; forced = true; }
         else if (v == "split" && p->pairing != MSFEC_RT_DQ) { ordering = 0; forced = true; }
-        else if (v == "nd" && p->pairing != MSFEC_RT_DQ) { ordering = 2; forced = true; }
+        else if (v == "nd") { ordering = 2; forced = true; }
       }
       std::string why;
       auto try_plan = [&](int ord, DirectPlan &out) {
@@ -224,7 +224,7 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
       bool have = try_plan(ordering, plan);
       // nested dissection only where the factorisation is flop-bound (>= 5 GFLOP per cell) and it saves >= 15 %: its many
       // small blocks mean more (and smaller) launches (C1, Q at n = 16: 0.6 GFLOP, 6.8 ms with layers/planes, 9.9 ms with ND)
-      if (!forced && p->pairing != MSFEC_RT_DQ && ((have && plan.update_flops >= 5e9) || !have)) {
+      if (!forced && ((have && plan.update_flops >= 5e9) || !have)) {
         DirectPlan nd;
         if (try_plan(2, nd) && (!have || nd.update_flops < 0.85 * plan.update_flops)) { plan = std::move(nd); have = true; }
       }

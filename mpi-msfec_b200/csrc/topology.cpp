@@ -551,8 +551,8 @@ DirectPlan build_direct_plan(const Topology &t, int ordering) {
     // Geometric nested dissection (doubled integer coordinates 0..2n): a box with more than kMinCells fine cells along
     // its longest axis is cut by the mesh plane through its middle; the two halves are eliminated first (recursively),
     // then the DoFs ON the cut as one block.  Every leading set of blocks is again a union of sub-box problems with
-    // essential conditions on the cuts, so the no-pivot argument of the layer/plane ordering carries over (not for
-    // RT_DQ, where a box interior alone is a pure-Neumann problem).  The separator planes are NOT dissected further:
+    // essential conditions on the cuts, so the no-pivot argument of the layer/plane ordering carries over (RT_DQ needs the
+    // cell hand-up described below).  The separator planes are NOT dissected further:
     // for Ned_RT a leading set that contains a plane only up to a line of fixed edge DoFs is a box with a slit spanning
     // two faces, which is not simply connected -- the Schur complement K A00^-1 K^T + A11 of that sub-problem has a
     // kernel and the pivots change sign (measured) -- and for Q_Ned the many small separator pieces cost more 32-padding
@@ -577,22 +577,42 @@ DirectPlan build_direct_plan(const Topology &t, int ordering) {
       std::sort(rows.begin(), rows.end());               // stacked numbering: sigma-type rows first
       slabs.push_back(rows);
     };
-    std::function<void(int[3], int[3], std::vector<int> &)> rec = [&](int lo[3], int hi[3], std::vector<int> &idx) {
+    // RT_DQ: with all faces of its boundary still uneliminated a box interior is a pure-Neumann problem (u is fixed up to
+    // a constant) and the last u pivot of the box would vanish.  Every box therefore hands ONE cell DoF up to the block
+    // of the plane that joins it with its sibling: there the first of the two handed-up cells is eliminated (the joined
+    // box still lacks the second one) and the second moves on to the next plane; the root's leftover is the pinned DoF.
+    const bool defer_u = t.pairing == MSFEC_RT_DQ;
+    std::function<int(int[3], int[3], std::vector<int> &)> rec = [&](int lo[3], int hi[3], std::vector<int> &idx) -> int {
       int d = -1, best = kMinCells;
       for (int a : {2, 1, 0}) if ((hi[a] - lo[a]) / 2 > best) { best = (hi[a] - lo[a]) / 2; d = a; }
-      if (d < 0 || (int)idx.size() <= PW) { emit(idx); return; }
+      if (d < 0 || (int)idx.size() <= PW) {
+        int deferred = -1;
+        if (defer_u) {
+          size_t at = 0;
+          for (size_t i = 0; i < idx.size(); ++i)
+            if (all[idx[i]].row >= NI0 && (deferred < 0 || all[idx[i]].row > all[deferred].row)) { deferred = idx[i]; at = i; }
+          if (deferred >= 0) idx.erase(idx.begin() + at);
+        }
+        emit(idx);
+        return deferred;
+      }
       const int mid = lo[d] + ((hi[d] - lo[d]) / 4) * 2;
       std::vector<int> L, R, Sp;
       for (int i : idx) (all[i].p[d] < mid ? L : all[i].p[d] > mid ? R : Sp).push_back(i);
       int l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
-      h2[d] = mid; rec(l2, h2, L);
-      h2[d] = hi[d]; l2[d] = mid; rec(l2, h2, R);
+      h2[d] = mid;
+      const int dl = rec(l2, h2, L);
+      h2[d] = hi[d]; l2[d] = mid;
+      const int dr = rec(l2, h2, R);
+      if (dl >= 0) Sp.push_back(dl);
       emit(Sp);
+      return dr;
     };
     std::vector<int> idx(all.size());
     for (size_t i = 0; i < all.size(); ++i) idx[i] = (int)i;
     int lo[3] = {0, 0, 0}, hi[3] = {2 * n, 2 * n, 2 * n};
-    rec(lo, hi, idx);
+    const int left_over = rec(lo, hi, idx);
+    if (left_over >= 0) { slabs.back().push_back(all[left_over].row); std::sort(slabs.back().begin(), slabs.back().end()); }
   } else {
     std::map<int, std::vector<int>> by_key;   // stacked interior row indices, sigma-type first
     for (int d = 0; d < NI0; ++d) by_key[key_of(0, d)].push_back(d);

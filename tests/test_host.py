@@ -183,15 +183,18 @@ def test_norm_operator_tables_match_oracle_gram_matrices(msfec, pairing):
         assert abs(G - G.T).max() == 0.0
 
 
-def test_direct_plan_nested_dissection(msfec, monkeypatch):
-    """The nested-dissection block ordering (chosen automatically at 4 local refinements for Q_Ned / Ned_RT, forced here at
-    3): the no-pivot LDL^T in the library's padded order reproduces the sparse-LU solution, pivots keep their signs
-    (positive on sigma-type, negative on u-type unknowns), and the symbolic structure differs from layers/planes."""
+@pytest.mark.parametrize("pairing,n_blocks,n_padded", [("NED_RT", 15, 2688), ("RT_DQ", 15, 2144)])
+def test_direct_plan_nested_dissection(msfec, monkeypatch, pairing, n_blocks, n_padded):
+    """The nested-dissection block ordering (chosen automatically at 4 local refinements for Q_Ned / Ned_RT / RT_DQ, forced
+    here at 3): the no-pivot LDL^T in the library's padded order reproduces the sparse-LU solution and pivots keep their
+    signs (positive on sigma-type, negative on u-type unknowns).  RT_DQ: every box hands one cell DoF up to the plane
+    that joins it with its sibling, otherwise the box interior is a pure-Neumann problem with a vanishing last pivot."""
     monkeypatch.setenv("MSFEC_DIRECT_ORDERING", "nd")
-    pairing, L, seed = "NED_RT", 3, 20261017
+    L = 3
+    seed = 20261017 if pairing == "NED_RT" else 0
     bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
     info = bb.table("direct.info")
-    assert int(info[2]) == 15 and int(info[3]) == 2688          # 8 boxes of 4^3 fine cells + 4 + 2 + 1 separator planes
+    assert (int(info[2]), int(info[3])) == (n_blocks, n_padded)   # 8 boxes of 4^3 fine cells + 4 + 2 + 1 separator planes
     cells = mo.morton_cells(2)
     prob = oracle_problem(pairing, L, random_seed=seed)
     M, r, Z, dbg = emulate.emulate_cell(bb, prob, cells[37], 37)
@@ -199,12 +202,15 @@ def test_direct_plan_nested_dissection(msfec, monkeypatch):
     h = (cells[37][7][0] - cells[37][0][0]) / D["n"]
     x, d, inv = emulate.emulate_direct(bb, dbg["vals"], h ** D["k_h_exponent"], dbg["b"])
     ref = dbg["x"]
-    assert np.abs(x - ref).max() <= 1e-9 * np.abs(ref).max()
+    sel = np.arange(D["NI0"]) if pairing == "RT_DQ" else np.arange(D["NI"])     # RT_DQ: u is fixed up to a constant
+    assert np.abs(x[sel] - ref[sel]).max() <= 1e-9 * np.abs(ref[sel]).max()
     real = inv >= 0
     is_u = np.zeros(len(inv), bool); is_u[real] = inv[real] >= D["NI0"]
     assert (d[real & ~is_u] > 0).all() and (d[real & is_u] < 0).all()
+    assert (d[~real] == -1.0).sum() == (1 if pairing == "RT_DQ" else 0)          # the pinned constant mode
     monkeypatch.delenv("MSFEC_DIRECT_ORDERING")
-    bb2 = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
-    assert int(bb2.table("direct.info")[3]) == 2656              # layers/planes stay the default at n = 8
+    if pairing == "NED_RT":
+        bb2 = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
+        assert int(bb2.table("direct.info")[3]) == 2656          # layers/planes stay the default at n = 8
     bb4 = msfec.BasisBuilder(lib_problem(msfec, pairing, 4), device=-1)
     assert int(bb4.table("direct.info")[2]) == 127               # nested dissection chosen at n = 16
