@@ -550,16 +550,14 @@ DirectPlan build_direct_plan(const Topology &t, int ordering) {
   if (ordering == 2) {
     // Geometric nested dissection (doubled integer coordinates 0..2n): a box with more than kMinCells fine cells along
     // its longest axis is cut by the mesh plane through its middle; the two halves are eliminated first (recursively),
-    // then the DoFs ON the cut as one block.  Every leading set of blocks is again a union of sub-box problems with
-    // essential conditions on the cuts, so the no-pivot argument of the layer/plane ordering carries over (RT_DQ needs the
-    // cell hand-up described below).  The separator planes are NOT dissected further:
-    // for Ned_RT a leading set that contains a plane only up to a line of fixed edge DoFs is a box with a slit spanning
-    // two faces, which is not simply connected -- the Schur complement K A00^-1 K^T + A11 of that sub-problem has a
-    // kernel and the pivots change sign (measured) -- and for Q_Ned the many small separator pieces cost more 32-padding
-    // than the fill they save (n = 16: 689 instead of 549 panels for the same 23.8 GFLOP).  Pays off from n = 16
-    // (Ned_RT: 35 instead of 51 GFLOP per cell, Q_Ned 24 instead of 34); at n = 8 the padding of the small blocks
-    // costs more than the fill it saves (profiles/ordering_model.py).
+    // then the DoFs ON the cut (split into pieces, see below).  Every leading set of blocks is again a union of sub-box
+    // problems with essential conditions on the cuts, so the no-pivot argument of the layer/plane ordering carries over
+    // (RT_DQ needs the cell hand-up described below).  Pays off from n = 16 (per cell: Q_Ned 14 instead of 34 GFLOP,
+    // Ned_RT 20 instead of 51, RT_DQ 3.5 instead of 34); at n = 8 the 32-padding of the small blocks costs more than the
+    // fill it saves (profiles/ordering_model.py).
     constexpr int kMinCells = 4;
+    int sep_piece = 8;                                     // min edge (fine cells) of a separator piece
+    if (const char *e = std::getenv("MSFEC_ND_SEP_PIECE")) sep_piece = std::max(1, std::atoi(e));
     struct Dof { int row; int p[3]; };
     std::vector<Dof> all;
     for (int b = 0; b < (t.two_blocks ? 2 : 1); ++b) {
@@ -604,8 +602,32 @@ DirectPlan build_direct_plan(const Topology &t, int ordering) {
       const int dl = rec(l2, h2, L);
       h2[d] = hi[d]; l2[d] = mid;
       const int dr = rec(l2, h2, R);
-      if (dl >= 0) Sp.push_back(dl);
-      emit(Sp);
+      // The plane is split into pieces of at least kSepPiece x kSepPiece fine cells along the cuts its two half boxes use
+      // next (a 16 x 16 plane into 4 quadrants), so that a box couples only with the pieces it touches.  The DoFs ON a
+      // dividing line go with the piece before it and the quadrants are taken in cyclic order: what is still fixed of the
+      // plane then always hangs on the outer boundary in one connected part, the leading sets stay simply connected
+      // (a separate block for the line would leave a slit spanning two faces -- the Ned_RT failure noted above).
+      int ax[2], na = 0, cut[2] = {0, 0};
+      for (int a = 0; a < 3; ++a) if (a != d) ax[na++] = a;
+      bool sp[2];
+      for (int i = 0; i < 2; ++i) {
+        sp[i] = (hi[ax[i]] - lo[ax[i]]) / 2 >= 2 * sep_piece;
+        cut[i] = lo[ax[i]] + ((hi[ax[i]] - lo[ax[i]]) / 4) * 2;
+      }
+      if (!sp[0] && !sp[1]) {
+        if (dl >= 0) Sp.push_back(dl);
+        emit(Sp);
+        return dr;
+      }
+      std::vector<int> piece[4];
+      for (int i : Sp) {
+        const int u = sp[0] && all[i].p[ax[0]] > cut[0], v = sp[1] && all[i].p[ax[1]] > cut[1];
+        piece[v ? (u ? 2 : 3) : (u ? 1 : 0)].push_back(i);          // cyclic: (0,0) (1,0) (1,1) (0,1)
+      }
+      int last = 0;
+      for (int q = 0; q < 4; ++q) if (!piece[q].empty()) last = q;
+      if (dl >= 0) piece[last].push_back(dl);
+      for (int q = 0; q < 4; ++q) emit(piece[q]);
       return dr;
     };
     std::vector<int> idx(all.size());

@@ -183,18 +183,22 @@ def test_norm_operator_tables_match_oracle_gram_matrices(msfec, pairing):
         assert abs(G - G.T).max() == 0.0
 
 
-@pytest.mark.parametrize("pairing,n_blocks,n_padded", [("NED_RT", 15, 2688), ("RT_DQ", 15, 2144)])
+@pytest.mark.parametrize("pairing,n_blocks,n_padded", [("NED_RT", 20, 2816), ("RT_DQ", 20, 2176)])
 def test_direct_plan_nested_dissection(msfec, monkeypatch, pairing, n_blocks, n_padded):
     """The nested-dissection block ordering (chosen automatically at 4 local refinements for Q_Ned / Ned_RT / RT_DQ, forced
     here at 3): the no-pivot LDL^T in the library's padded order reproduces the sparse-LU solution and pivots keep their
     signs (positive on sigma-type, negative on u-type unknowns).  RT_DQ: every box hands one cell DoF up to the plane
-    that joins it with its sibling, otherwise the box interior is a pure-Neumann problem with a vanishing last pivot."""
+    that joins it with its sibling, otherwise the box interior is a pure-Neumann problem with a vanishing last pivot.
+    Separator planes are split into quadrants (here 4 x 4 fine cells so that n = 8 exercises it; 8 x 8 in production) with
+    the dividing lines attached to the earlier quadrant, in cyclic order -- the variant whose leading sets stay simply
+    connected (a separate block for the lines makes Ned_RT pivots change sign)."""
     monkeypatch.setenv("MSFEC_DIRECT_ORDERING", "nd")
+    monkeypatch.setenv("MSFEC_ND_SEP_PIECE", "4")
     L = 3
     seed = 20261017 if pairing == "NED_RT" else 0
     bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
     info = bb.table("direct.info")
-    assert (int(info[2]), int(info[3])) == (n_blocks, n_padded)   # 8 boxes of 4^3 fine cells + 4 + 2 + 1 separator planes
+    assert (int(info[2]), int(info[3])) == (n_blocks, n_padded)   # 8 boxes of 4^3 fine cells + 4 + 2 x 2 + 4 plane pieces
     cells = mo.morton_cells(2)
     prob = oracle_problem(pairing, L, random_seed=seed)
     M, r, Z, dbg = emulate.emulate_cell(bb, prob, cells[37], 37)
@@ -209,8 +213,9 @@ def test_direct_plan_nested_dissection(msfec, monkeypatch, pairing, n_blocks, n_
     assert (d[real & ~is_u] > 0).all() and (d[real & is_u] < 0).all()
     assert (d[~real] == -1.0).sum() == (1 if pairing == "RT_DQ" else 0)          # the pinned constant mode
     monkeypatch.delenv("MSFEC_DIRECT_ORDERING")
+    monkeypatch.delenv("MSFEC_ND_SEP_PIECE")
     if pairing == "NED_RT":
         bb2 = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
         assert int(bb2.table("direct.info")[3]) == 2656          # layers/planes stay the default at n = 8
     bb4 = msfec.BasisBuilder(lib_problem(msfec, pairing, 4), device=-1)
-    assert int(bb4.table("direct.info")[2]) == 127               # nested dissection chosen at n = 16
+    assert int(bb4.table("direct.info")[2]) == 132               # nested dissection chosen at n = 16 (127 + 3 + 2 pieces)
