@@ -85,7 +85,9 @@ typedef struct msfec_stats {
   int32_t kernel_launches;       /* kernels launched by the last build               */
   int32_t reserved;
   double iterations_mean;
-  double residual_max;           /* max final relative (preconditioned) residual     */
+  double residual_max;           /* MINRES: max final relative preconditioned residual;
+                                  * direct: max over cells of the TRUE relative residual
+                                  * of a fixed generic combination of the k rhs        */
   double ms_assemble, ms_lift, ms_solve, ms_gram, ms_total;   /* CUDA-event times    */
   double krylov_matrix_bytes;    /* algorithmic bytes of the Krylov kernel*/
   double krylov_ms_spmm;         /* device time inside the SpMM kernel               */
