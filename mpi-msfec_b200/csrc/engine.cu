@@ -1396,7 +1396,8 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
                 T_.two_blocks ? T_.blk[1].n_total : 0, T_.blk[0].n_total - T_.blk[0].n_int, T_.NI, T_.NB, T_.NF,
                 T_.k_solve, kg, T_.k0, T_.pairing == MSFEC_RT_DQ ? 1 : 0};
     k_finalize_basis<<<dim3((T_.NF + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(D, d_vec_[7], d_G_, d_Z_, gz0);
-    k_apply_full<<<dim3((T_.NF + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(full_.dev, T_.NF, T_.blk[0].n_total, T_.k0, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
+    static const int apply_rows = std::getenv("MSFEC_APPLY_ROWS") ? std::max(1, std::min(32, std::atoi(std::getenv("MSFEC_APPLY_ROWS")))) : 4;
+    k_apply_full<<<dim3((T_.NF + apply_rows - 1) / apply_rows, groups), dim3(kLanes, apply_rows), 0, stream_>>>(full_.dev, T_.NF, T_.blk[0].n_total, T_.k0, kg, n_slots_, kscale, d_vals_, d_Z_, gz0, d_Y_);
     const int rhs_off = T_.rhs_block ? T_.blk[0].n_total : 0;
     {
       // d-slices per group: the count <= 16 that fills whole waves of 2 CTAs/SM best (3 slices x 128 groups = 384 CTAs
