@@ -250,3 +250,24 @@ def test_minres_full_size(msfec, pairing):
     worst = _check_cells(bb, oracle_problem(pairing, 4), cells, np.arange(32), (5,))
     print(pairing, "L=4 minres worst", worst, bb.stats["iterations_max"])
     assert worst < TOL and bb.stats["solver"] == 0
+
+
+def test_bench_line_contract(tmp_path):
+    """bench.py prints exactly ONE JSON line on stdout with the keys the driver reads (small workload)."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--cells", "96", "--steps", "1", "--warmup", "3",
+                        "--cpu-sample", "16"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["dtype"] == "f64" and d["unit"] == "coarse cells/s" and d["value"] > 0 and d["gpu_launches"] > 0
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
+    assert "workload" in d["config"] and d["krylov"]["residual_max"] < 1e-10
