@@ -329,7 +329,7 @@ k_direct_region(double *__restrict__ band, size_t band_stride, long long col_off
 // Shared memory: max(np, 2) blocks of 32 x 36 doubles (V_p + one per block row below; the first of those holds the
 // rows of L_pp while V_p is computed).   grid (cells), block 32, dynamic shared memory region_mma_smem(np)
 constexpr int kRMLd = kDP + 4;                     // row stride 36 = 4 mod 16: conflict-free fragment loads
-constexpr size_t region_mma_smem(int np) { return ((size_t)(np < 2 ? 2 : np) * kDP * kRMLd + 3 * kDP) * sizeof(double); }
+constexpr size_t region_mma_smem(int np, bool keep_x) { return ((size_t)(keep_x ? (np < 2 ? 2 : np) : 3) * kDP * kRMLd + 4 * kDP) * sizeof(double); }
 
 __device__ __forceinline__ double rcp_newton(double d) {
   double r;
@@ -340,14 +340,18 @@ __device__ __forceinline__ double rcp_newton(double d) {
   return r;
 }
 
+// KEEP_X = true: the X blocks of all block rows below the panel stay in shared memory (np blocks of 9 KB: 7 CTAs/SM at
+// np = 3 but only 4 at np = 5).  KEEP_X = false: three blocks for any np -- the updates re-stage L_qp / L_q2p from the
+// band (L2 hits) and form X = L D in the fragment load, which keeps 7 warps per SM for the 5-panel chunks.
+template <bool KEEP_X>
 __global__ void __launch_bounds__(32, 8)
 k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col_off, int ld, int j0, int np, int pglob0,
                     int NP, double *__restrict__ dvec, double *__restrict__ vinv, int *__restrict__ bad) {
   extern __shared__ __align__(16) double rm_smem[];
   double *Vs = rm_smem;                                   // [32][36]  V_p(i, j)
   double *S1 = rm_smem + kDP * kRMLd;                     // [np-1][32][36]  L_pp rows, then X blocks of rows q > p
-  double *colb = rm_smem + (size_t)(np < 2 ? 2 : np) * kDP * kRMLd;      // [2][32]
-  double *dsm = colb + 2 * kDP;                           // [32]  1/d of the current panel
+  double *colb = rm_smem + (size_t)(KEEP_X ? (np < 2 ? 2 : np) : 3) * kDP * kRMLd;      // [2][32]
+  double *dsm = colb + 2 * kDP;                           // [2][32]  1/d and d of the current panel
   const int cell = blockIdx.x, lane = threadIdx.x;
   const int fr = lane >> 2, fk = lane & 3;
   double *P = band + (size_t)cell * band_stride + col_off;
@@ -380,6 +384,7 @@ k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col
       }
       dvec[(size_t)cell * NP + pglob0 + p * kDP + lane] = my_d;
       dsm[lane] = 1.0 / my_d;
+      dsm[kDP + lane] = my_d;
 #pragma unroll
       for (int k = 0; k < kDP; ++k) S1[lane * kRMLd + k] = (k < lane) ? a[k] : 0.0;
     }
@@ -414,10 +419,10 @@ k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col
 #pragma unroll
     for (int t = 0; t < 4; ++t) dinv_m[t] = dsm[t * 8 + fr];
 #pragma unroll
-    for (int ks = 0; ks < kDP / 4; ++ks) ndinv_k[ks] = -dsm[ks * 4 + fk];
+    for (int ks = 0; ks < kDP / 4; ++ks) ndinv_k[ks] = KEEP_X ? -dsm[ks * 4 + fk] : -dsm[kDP + ks * 4 + fk];   // -1/d_k | -d_k
     // ---- blocks below: X_qp = A_qp V_p^T ----------------------------------------------------------------
     for (int q = p + 1; q < np; ++q) {
-      double *Xq = S1 + (size_t)(q - p - 1) * kDP * kRMLd;
+      double *Xq = S1 + (KEEP_X ? (size_t)(q - p - 1) * kDP * kRMLd : 0);
       {
         const double *B = P + (size_t)jp * ld + j0 + q * kDP + lane;       // row `lane` of A_qp
 #pragma unroll
@@ -448,8 +453,10 @@ k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int k = mt * 8 + fr, i = nt * 8 + fk * 2;
-          Xq[i * kRMLd + k] = acc[mt][nt][0];
-          Xq[(i + 1) * kRMLd + k] = acc[mt][nt][1];
+          if (KEEP_X) {
+            Xq[i * kRMLd + k] = acc[mt][nt][0];
+            Xq[(i + 1) * kRMLd + k] = acc[mt][nt][1];
+          }
           *reinterpret_cast<double2 *>(P + (size_t)(jp + k) * ld + j0 + q * kDP + i) =
               make_double2(acc[mt][nt][0] * dinv_m[mt], acc[mt][nt][1] * dinv_m[mt]);
         }
@@ -457,9 +464,24 @@ k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col
     __syncwarp();
     // ---- right-looking update of the rest of the region: C(q2, q) -= X_q2p L_qp^T ----------------------------
     for (int q = p + 1; q < np; ++q) {
-      const double *Lq = S1 + (size_t)(q - p - 1) * kDP * kRMLd;            // X_qp; L = X D^-1 in the fragment load
+      const double *Lq = S1 + (KEEP_X ? (size_t)(q - p - 1) * kDP * kRMLd : 0);   // X_qp (KEEP_X) or L_qp
+      if (!KEEP_X) {
+        __syncwarp();                                                          // previous readers of both slots are done
+        const double *B = P + (size_t)jp * ld + j0 + q * kDP + lane;           // row `lane` of L_qp
+#pragma unroll
+        for (int k = 0; k < kDP; ++k) S1[lane * kRMLd + k] = B[(size_t)k * ld];
+        __syncwarp();
+      }
       for (int q2 = q; q2 < np; ++q2) {
-        const double *Xq2 = S1 + (size_t)(q2 - p - 1) * kDP * kRMLd;
+        const double *Xq2 = S1 + (KEEP_X ? (size_t)(q2 - p - 1) * kDP * kRMLd : (q2 == q ? 0 : (size_t)kDP * kRMLd));
+        if (!KEEP_X && q2 != q) {
+          __syncwarp();
+          double *S2 = S1 + (size_t)kDP * kRMLd;
+          const double *B = P + (size_t)jp * ld + j0 + q2 * kDP + lane;        // row `lane` of L_q2p
+#pragma unroll
+          for (int k = 0; k < kDP; ++k) S2[lane * kRMLd + k] = B[(size_t)k * ld];
+          __syncwarp();
+        }
         double *C = P + (size_t)(j0 + q * kDP + fr) * ld + j0 + q2 * kDP + fk * 2;
         const bool dg = q2 == q;
         double acc[4][4][2];
@@ -476,8 +498,13 @@ k_direct_region_mma(double *__restrict__ band, size_t band_stride, long long col
           double af[4], bf[4];
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            af[t] = Lq[(t * 8 + fr) * kRMLd + ks * 4 + fk] * ndinv_k[ks];                   // A[m = j][k] = -L(j, k)
-            bf[t] = Xq2[(t * 8 + fr) * kRMLd + ks * 4 + fk];                                // B[k][n = i] = X(i, k)
+            if (KEEP_X) {
+              af[t] = Lq[(t * 8 + fr) * kRMLd + ks * 4 + fk] * ndinv_k[ks];                 // A[m = j][k] = -L(j, k) = -X(j, k) / d_k
+              bf[t] = Xq2[(t * 8 + fr) * kRMLd + ks * 4 + fk];                              // B[k][n = i] = X(i, k)
+            } else {
+              af[t] = Lq[(t * 8 + fr) * kRMLd + ks * 4 + fk];                               // A[m = j][k] = L(j, k)
+              bf[t] = Xq2[(t * 8 + fr) * kRMLd + ks * 4 + fk] * ndinv_k[ks];                // B[k][n = i] = -X(i, k) = -L(i, k) d_k
+            }
           }
 #pragma unroll
           for (int mt = 0; mt < 4; ++mt)

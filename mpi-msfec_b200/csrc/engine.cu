@@ -849,7 +849,9 @@ class Engine {
       CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
       if (const char *b = std::getenv("MSFEC_DIRECT_TRSM_ROWS")) { const int v = std::atoi(b); trsm_rows_ = v == 32 ? 32 : (v == 648 ? 648 : 64); }
       if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_REGION")) fused_region_ = std::max(0, std::min(2, std::atoi(b)));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow, true)));
+      CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow, false)));
+      if (const char *b = std::getenv("MSFEC_DIRECT_REGION_KEEPX")) region_keepx_max_np_ = std::atoi(b);
       if (const char *b = std::getenv("MSFEC_DIRECT_LANES")) kDirectLanes = std::max(1, std::min(kMaxDirectLanes, std::atoi(b)));
       {
         // MSFEC_DIRECT_PRIO=1: descending stream priorities (lane 0 highest), so the later lanes fill the gaps
@@ -958,6 +960,9 @@ class Engine {
   bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
   int fused_region_ = 2;                     // diagonal region of a chunk in one launch: MSFEC_DIRECT_FUSED_REGION = 0 (per-panel
                                              // launches) | 1 (one warp per cell, FMA) | 2 (one warp per cell, DMMA block products)
+  int region_keepx_max_np_ = 6;              // chunks of up to this many panels keep their X blocks in shared memory
+                                             // (MSFEC_DIRECT_REGION_KEEPX; wider chunks re-stage L from the band: 3 smem blocks for any
+                                             // np, 7 instead of 4 warps/SM at np = 5 -- measured 10.07 vs 9.93 ms, no gain)
   int trsm_rows_ = 32;                       // k_direct_trsm tile: MSFEC_DIRECT_TRSM_ROWS = 32 (4 warps) | 64 (4 warps) | 648 (64 rows, 8 warps)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
   // sub-batches can be processed round-robin on several streams ("lanes") with private band storage; measured on
@@ -1218,8 +1223,12 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
         if (fused_region_) {
           // one warp per cell factors the whole diagonal region of the chunk
           if (fused_region_ == 2)
-            k_direct_region_mma<<<nc, 32, region_mma_smem(np), stream_>>>(
-                d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
+            if (np <= region_keepx_max_np_)
+              k_direct_region_mma<true><<<nc, 32, region_mma_smem(np, true), stream_>>>(
+                  d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
+            else
+              k_direct_region_mma<false><<<nc, 32, region_mma_smem(np, false), stream_>>>(
+                  d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
           else
             k_direct_region<<<(nc + kRegionWarps - 1) / kRegionWarps, 32 * kRegionWarps, 0, stream_>>>(
                 d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, nc, d_dvec_, d_vinv_, d_flag_ + 2);
