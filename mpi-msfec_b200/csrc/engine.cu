@@ -87,9 +87,9 @@ __global__ void k_sample_coefficients(CoefParams P, const ExprInstr *__restrict_
   const double pz = x0[(g * 3 + 2) * kLanes + lane] + h * (ck + gq[q >> 2]);
   double *o = coef + ((size_t)(g * P.nC + T) * 56 + q * 7) * kLanes + lane;
   if (P.use_random) {
-    // piecewise constant per fine cell: the 8 Gauss points share one sample, so one warp evaluates the
-    // normals / exponentials / rotation and the other seven copy the 7 channels from shared memory
-    __shared__ double ch[7][kLanes];
+    // cell-wise constant field: the 8 Gauss points share one sample, so only the q = 0 warp evaluates it and ONE copy of
+    // the 7 channels is stored per fine cell (layout [g][fine cell][7][32]); the slot assembly then uses pair tables with
+    // the 8 quadrature weights already summed (Engine::collapse_pairs)
     if (q == 0) {
       double xi[4], d[3];
       field_normals(P.seed, (unsigned long long)gid[g * kLanes + lane] * (unsigned long long)P.nC + T, xi);
@@ -97,18 +97,16 @@ __global__ void k_sample_coefficients(CoefParams P, const ExprInstr *__restrict_
       double s = exp(P.sigma * xi[3]);
       if (P.tensor_inverse) { d[0] = 1.0 / d[0]; d[1] = 1.0 / d[1]; d[2] = 1.0 / d[2]; }
       if (P.scalar_inverse) s = 1.0 / s;
+      double *oc = coef + ((size_t)(g * P.nC + T) * 7) * kLanes + lane;
       int c = 0;
 #pragma unroll
       for (int a = 0; a < 3; ++a)
 #pragma unroll
         for (int b = a; b < 3; ++b)
-          ch[c++][lane] = P.rot[a * 3 + 0] * d[0] * P.rot[b * 3 + 0] + P.rot[a * 3 + 1] * d[1] * P.rot[b * 3 + 1] +
-                          P.rot[a * 3 + 2] * d[2] * P.rot[b * 3 + 2];
-      ch[6][lane] = s;
+          oc[(c++) * kLanes] = P.rot[a * 3 + 0] * d[0] * P.rot[b * 3 + 0] + P.rot[a * 3 + 1] * d[1] * P.rot[b * 3 + 1] +
+                               P.rot[a * 3 + 2] * d[2] * P.rot[b * 3 + 2];
+      oc[6 * kLanes] = s;
     }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 7; ++c) o[c * kLanes] = ch[c][lane];
   } else {
     double d[3], s;
     d[0] = P.a_scale[0] * (1.0 - P.a_alpha[0] * sin(2.0 * M_PI * P.a_freq[0] * px));
@@ -797,6 +795,7 @@ class Engine {
     for (auto &ev : ev_sp_) CUDA_OK(cudaEventCreate(&ev));
     sys_.upload(T_.sys); lift_.upload(T_.lift); full_.upload(T_.full); kint_.upload(T_.kint);
     asm00_.upload(T_.asm00); asm11_.upload(T_.asm11); asmrhs_.upload(T_.asm_rhs);
+    if (spec_.coef.use_random) { asm00c_.upload(collapse_pairs(T_.asm00)); asm11c_.upload(collapse_pairs(T_.asm11)); }
     d_diag0_ = dev_upload(T_.diag_slot0); d_diag1_ = dev_upload(T_.diag_slot1);
     d_G_ = dev_upload(T_.G); d_F1_ = dev_upload(T_.F1);
     d_prog_ = dev_upload(spec_.programs);
@@ -885,7 +884,7 @@ class Engine {
     cudaFree(d_dp_cdest_); cudaFree(d_dp_cref_); cudaFree(d_dp_sdest_); cudaFree(d_dp_sval_); cudaFree(d_dp_kdest_);
     cudaFree(d_dp_kval_); cudaFree(d_dp_rhs_); cudaFree(d_dp_code_);
     sys_.release(); lift_.release(); full_.release(); kint_.release();
-    asm00_.release(); asm11_.release(); asmrhs_.release();
+    asm00_.release(); asm11_.release(); asmrhs_.release(); asm00c_.release(); asm11c_.release();
     cudaFree(d_diag0_); cudaFree(d_diag1_); cudaFree(d_G_); cudaFree(d_F1_); cudaFree(d_prog_);
     for (auto &N : norm_) { cudaFree(N.ptr); cudaFree(N.col); cudaFree(N.val); }
     cudaFree(d_norm_part_); cudaFree(d_norm_out_);
@@ -922,6 +921,8 @@ class Engine {
   double cell_iters_ = 0;
   OpStore sys_, lift_, full_, kint_;
   AsmStore asm00_, asm11_, asmrhs_;
+  AsmStore asm00c_, asm11c_;                // pair tables summed over the quadrature points (cell-wise constant coefficients)
+  static AsmTable collapse_pairs(const AsmTable &a);
   int *d_diag0_ = nullptr, *d_diag1_ = nullptr;
   double *d_G_ = nullptr, *d_F1_ = nullptr;
   ExprInstr *d_prog_ = nullptr;
@@ -1103,6 +1104,24 @@ int Engine::solve_batch(int groups, int n_valid, double kscale, msfec_stats &st,
   return it;
 }
 
+
+// Pair tables for coefficients that are constant on every fine cell (the synthetic random field): the entries of a
+// pair list that differ only in the quadrature point are merged, channel index = component (0..6), weight = sum over q.
+// 8x fewer coefficient reads in k_assemble_slots and one coefficient copy per fine cell instead of eight.
+AsmTable Engine::collapse_pairs(const AsmTable &a) {
+  AsmTable c = a;
+  const int ncomp = a.coef_stride / 8;
+  c.coef_stride = ncomp;
+  c.pair_ptr.assign(1, 0); c.pair_idx.clear(); c.pair_w.clear();
+  for (size_t p = 0; p + 1 < a.pair_ptr.size(); ++p) {
+    std::vector<double> w(ncomp, 0.0);
+    std::vector<char> used(ncomp, 0);
+    for (int e = a.pair_ptr[p]; e < a.pair_ptr[p + 1]; ++e) { w[a.pair_idx[e] % ncomp] += a.pair_w[e]; used[a.pair_idx[e] % ncomp] = 1; }
+    for (int k = 0; k < ncomp; ++k) if (used[k]) { c.pair_idx.push_back(k); c.pair_w.push_back(w[k]); }
+    c.pair_ptr.push_back((int32_t)c.pair_idx.size());
+  }
+  return c;
+}
 
 void Engine::free_direct() {
   for (auto &L : lane_) {
@@ -1380,12 +1399,13 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     CUDA_OK(cudaEventRecord(ev_[0], stream_));
     k_prepare_cells<<<(groups * kLanes + 127) / 128, 128, 0, stream_>>>(dc, dids, cell0, nb, n_cells, H, d_x0_, d_gid_, d_flag_ + 1);
     k_sample_coefficients<<<dim3(T_.nC, groups), dim3(kLanes, 8), 0, stream_>>>(spec_.coef, d_prog_, d_x0_, d_gid_, h, d_coef_, d_fr_);
+    const bool cellwise = spec_.coef.use_random != 0;
     k_assemble_slots<<<dim3((T_.asm00.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
-        asm00_.dev, T_.nC, d_coef_, std::pow(h, T_.asm00.h_exponent) / 8.0, d_vals_, n_slots_, 0);
+        cellwise ? asm00c_.dev : asm00_.dev, T_.nC, d_coef_, std::pow(h, T_.asm00.h_exponent) / 8.0, d_vals_, n_slots_, 0);
     launches_ += 3;
     if (T_.asm11.n_slots) {
       k_assemble_slots<<<dim3((T_.asm11.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
-          asm11_.dev, T_.nC, d_coef_, std::pow(h, T_.asm11.h_exponent) / 8.0, d_vals_, n_slots_, T_.n_slots0);
+          cellwise ? asm11c_.dev : asm11_.dev, T_.nC, d_coef_, std::pow(h, T_.asm11.h_exponent) / 8.0, d_vals_, n_slots_, T_.n_slots0);
       ++launches_;
     }
     k_assemble_slots<<<dim3((T_.asm_rhs.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
