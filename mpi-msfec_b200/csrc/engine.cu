@@ -572,7 +572,9 @@ __global__ void k_apply_full(OpDev A, int NF, int N0, int k0, int kg, int n_slot
 constexpr int kGramDT = 8;                     // fine DoFs per staged tile
 constexpr int kGramJ = 24;                     // k padded to 3 MMA tiles
 constexpr int kGramCS = kGramDT * kGramJ + 1;  // per-cell stride in shared memory (odd)
-__global__ void __launch_bounds__(256)
+constexpr int kGramWarps = 16;                 // 512 threads: 2 cells per warp (72 accumulator registers); 8 warps x 4 cells
+                                               // needed 207 registers, i.e. one CTA of 8 warps per SM and nothing to hide the staging
+__global__ void __launch_bounds__(32 * kGramWarps)
 k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double *__restrict__ Y,
             const double *__restrict__ grhs, int rhs_off, int n_rhs, int n_slices,
             double *__restrict__ Mpart, double *__restrict__ rpart) {
@@ -584,19 +586,20 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
   const int d_lo = slice * per, d_hi = min(NF, d_lo + per);
   const double *z = Z + (size_t)(gz0 + g) * NF * kg * kLanes;
   const double *y = Y + (size_t)g * NF * kg * kLanes;
-  double acc[4][3][3][2];
+  constexpr int CPW = kLanes / kGramWarps, NT = 32 * kGramWarps;   // cells per warp, threads
+  double acc[CPW][3][3][2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < CPW; ++c)
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b) acc[c][a][b][0] = acc[c][a][b][1] = 0.0;
   double racc = 0.0;                                       // rhs: thread (cell = lane, i = warp + 8*q) handled below
-  for (int idx = tid; idx < kLanes * kGramCS; idx += 256) { Zs[idx] = 0.0; Ys[idx] = 0.0; }   // zero the j padding once
+  for (int idx = tid; idx < kLanes * kGramCS; idx += NT) { Zs[idx] = 0.0; Ys[idx] = 0.0; }   // zero the j padding once
   __syncthreads();
   for (int d0 = d_lo; d0 < d_hi; d0 += kGramDT) {
     // stage: element (dd, j, cell) ; consecutive threads -> consecutive cells (coalesced 256 B global reads)
-    for (int idx = tid; idx < kGramDT * kg * kLanes; idx += 256) {
+    for (int idx = tid; idx < kGramDT * kg * kLanes; idx += NT) {
       const int cell = idx & 31, t = idx >> 5, j = t % kg, dd = t / kg;
       const bool ok = d0 + dd < d_hi;
       const size_t o = ((size_t)(d0 + dd) * kg + j) * kLanes + cell;
@@ -605,8 +608,8 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
     }
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const double *zc = Zs + (warp + 8 * c) * kGramCS, *yc = Ys + (warp + 8 * c) * kGramCS;
+    for (int c = 0; c < CPW; ++c) {
+      const double *zc = Zs + (warp + kGramWarps * c) * kGramCS, *yc = Ys + (warp + kGramWarps * c) * kGramCS;
 #pragma unroll
       for (int ks = 0; ks < kGramDT / 4; ++ks) {
         double af[3], bf[3];
@@ -625,8 +628,8 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
   }
   // partial M: Mpart[slice][cell in batch][24][24]
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    double *mp = Mpart + (((size_t)slice * gridDim.x + g) * kLanes + warp + 8 * c) * kGramJ * kGramJ;
+  for (int c = 0; c < CPW; ++c) {
+    double *mp = Mpart + (((size_t)slice * gridDim.x + g) * kLanes + warp + kGramWarps * c) * kGramJ * kGramJ;
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -635,7 +638,7 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
         for (int h = 0; h < 2; ++h) mp[(a * 8 + fr) * kGramJ + b * 8 + fk * 2 + h] = acc[c][a][b][h];
   }
   // coarse rhs (tiny): thread (lane = cell, i = warp + 8 q), slice of the rhs block rows
-  for (int i = warp; i < kg; i += 8) {
+  for (int i = warp; i < kg; i += kGramWarps) {
     racc = 0.0;
     for (int d = max(d_lo, rhs_off); d < min(d_hi, rhs_off + n_rhs); ++d)
       racc = fma(z[((size_t)d * kg + i) * kLanes + lane], grhs[((size_t)g * n_rhs + d - rhs_off) * kLanes + lane], racc);
@@ -1446,7 +1449,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
         gram_part_size_ = need;
       }
       double *Mpart = d_gram_part_, *rpart = d_gram_part_ + (size_t)n_slices * groups * kLanes * kGramJ * kGramJ;
-      k_gram_dmma<<<dim3(groups, n_slices), 256, 2 * kLanes * kGramCS * sizeof(double), stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
+      k_gram_dmma<<<dim3(groups, n_slices), 32 * kGramWarps, 2 * kLanes * kGramCS * sizeof(double), stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
                                                             n_slices, Mpart, rpart);
       k_gram_reduce<<<nb, 128, 0, stream_>>>(kg, groups, n_slices, cell0, n_cells, Mpart, rpart, d_M_, d_r_);
       ++launches_;
