@@ -952,7 +952,8 @@ class Engine {
   long launches_ = 0;
   // direct solver
   bool use_direct_ = false;
-  int direct_sub_ = 0;                       // cells per direct sub-batch (allocated)
+  int direct_sub_ = 0;                       // cells per direct sub-batch (step; multiple of 32)
+  long direct_alloc_ = 0;                    // cells the lane buffers are allocated for
   int ldy_ = 0;                              // row stride of the window scratch (max front height)
   int direct_chunk_ = 5;                     // max panels per chunk (K = 32 * chunk for the update behind a chunk); 5-panel blocks
                                              // go as one chunk, 6-panel blocks as 3 + 3 (measured: 3/4/5/6 -> 35.8/35.8/36.3/35.6 k cells/s)
@@ -1131,7 +1132,7 @@ void Engine::free_direct() {
     cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT); cudaFree(L.ybuf); cudaFree(L.vinv);
     L.band = L.diagL = L.dvec = L.xT = L.ybuf = L.vinv = nullptr;
   }
-  direct_sub_ = 0;
+  direct_sub_ = 0; direct_alloc_ = 0;
 }
 
 void Engine::alloc_direct(int nb) {
@@ -1143,8 +1144,13 @@ void Engine::alloc_direct(int nb) {
   sub = std::max(32L, sub / 32 * 32);
   sub = std::min<long>(sub, ((nb + kDirectLanes - 1) / kDirectLanes + 31) / 32 * 32);
   sub = std::min<long>(sub, 65535 / 32 * 32);
-  if (sub <= direct_sub_) return;
+  // the sub-batch step never shrinks; memory is reserved for the cells that are resident at once, min(step, nb) -- at 5 local
+  // refinements one Ned_RT band is 2.8 GB, so a 3-cell build must not reserve the 32-cell minimum step (90 GB)
+  const long step = std::max<long>(sub, direct_sub_);
+  const long need = std::min<long>(step, nb);
+  if (need <= direct_alloc_) { direct_sub_ = (int)step; return; }
   free_direct();
+  sub = need;
   for (int i = 0; i < kDirectLanes; ++i) {
     auto &L = lane_[i];
     CUDA_OK(cudaMalloc(&L.band, (size_t)sub * P_.band_doubles * sizeof(double)));
@@ -1154,6 +1160,8 @@ void Engine::alloc_direct(int nb) {
     CUDA_OK(cudaMalloc(&L.xT, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.ybuf, (size_t)sub * kMaxWindow * kDP * ldy_ * sizeof(double)));
   }
+  direct_alloc_ = need;
+  sub = step;
   direct_sub_ = (int)sub;
 }
 

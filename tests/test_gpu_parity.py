@@ -271,3 +271,26 @@ def test_bench_line_contract(tmp_path):
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
     assert set(("value", "unit", "cores", "kind", "sample")) <= set(d["cpu_baseline"])
     assert "workload" in d["config"] and d["krylov"]["residual_max"] < 1e-10
+
+
+@pytest.mark.parametrize("pairing", ["Q", "NED_RT"])
+def test_five_local_refinements_direct(msfec, pairing):
+    """Largest local size (n = 32: 35 937 / 206 976 fine DoFs per cell).  The layer/plane band of Ned_RT exceeds 2^31 entries
+    per cell there; the nested-dissection plan fits.  Checked by size-independent properties: true residual of every cell,
+    partition of unity (rows of the Q matrix sum to zero), the symmetry pattern of M, independence of the batch composition."""
+    cells = mo.morton_cells(2)[:3]
+    ids = np.arange(3)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, 5, use_direct_solver_basis=1), device=0).run(cells, ids)
+    st = bb.stats
+    assert st["not_converged"] == 0 and st["residual_max"] < 1e-10
+    M = bb.get_global_element_matrix().copy()
+    k0 = 8 if pairing == "Q" else 12
+    scale = np.abs(M).max()
+    assert np.abs(M[:, :k0, :k0] - M[:, :k0, :k0].transpose(0, 2, 1)).max() < 1e-11 * scale
+    if pairing == "Q":
+        assert np.abs(M.sum(2)).max() < 1e-10 * scale
+    else:
+        assert np.abs(M[:, k0:, k0:] - M[:, k0:, k0:].transpose(0, 2, 1)).max() < 1e-11 * scale
+        assert np.abs(M[:, :k0, k0:] + M[:, k0:, :k0].transpose(0, 2, 1)).max() < 1e-11 * scale
+    bb2 = msfec.BasisBuilder(lib_problem(msfec, pairing, 5, use_direct_solver_basis=1), device=0).run(cells[2:3], ids[2:3])
+    assert np.abs(bb2.get_global_element_matrix()[0] - M[2]).max() < 1e-12 * scale
