@@ -172,8 +172,9 @@ def main():
     ap.add_argument("--local-refinements", type=int, default=3)
     ap.add_argument("--cells", type=int, default=0, help="use only the first C coarse cells (debug)")
     ap.add_argument("--cells-per-batch", type=int, default=0)
-    ap.add_argument("--solver", default="direct", choices=["direct", "minres"],
-                    help="'use direct solver basis' true (batched block LDL^T) / false (batched MINRES)")
+    ap.add_argument("--solver", default="auto", choices=["auto", "mf", "band", "minres"],
+                    help="solver of the local problems (msfec_problem.solver); auto = what a verbatim .prm gets: "
+                         "multifrontal LDL^T up to 3 local refinements, banded block LDL^T beyond")
     ap.add_argument("--cpu-sample", type=int, default=0, help="cells in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -189,7 +190,7 @@ def main():
     workload = (f"synthetic 3D Ned_RT, rough random field (seed {SEED}, sigma ln(10)/2), "
                 f"{n_total} coarse cells (global refinements {g_ref}) x {L} local refinements")
     config = {"workload": workload, "pairing": "NED_RT", "coarse_cells": n_total, "local_refinements": L,
-              "use_direct_solver_basis": args.solver == "direct",
+              "use_direct_solver_basis": False, "solver": args.solver,
               "partition": f"contiguous Morton chunks over {world} rank(s)",
               "cache": "inputs larger than L2 (per-step working set is GBs)"}
 
@@ -229,7 +230,7 @@ def main():
     ids = np.arange(lo, hi, dtype=np.int64)
     prob = m.make_problem("NED_RT", n_refine_local=L, n_refine_global=g_ref, random_field_seed=SEED,
                           rhs_expression=RHS, rhs_constants="scale=100", cells_per_batch=args.cells_per_batch,
-                          use_direct_solver_basis=1 if args.solver == "direct" else 0)
+                          use_direct_solver_basis=0, solver=m.SOLVER[args.solver])
     bb = m.BasisBuilder(prob, device=local_rank)
     dev = torch.device("cuda", local_rank)
     # device-resident inputs/outputs for `value`; pinned host buffers for `e2e`
@@ -288,7 +289,32 @@ def main():
         e2e_value = n_total / (e_wall_ms / args.steps * 1e-3)
         st = stats[-1]
         n_fine_dofs = st["n_fine_dofs"]
-        if args.solver == "minres":
+        solver_used = {0: "minres", 1: "band", 2: "mf"}[st["solver"]]
+        hbm_pk, hbm_src = hbm_peak()
+        if solver_used == "mf":
+            # dominant kernel k_mf_forward (one CTA per front, fronts in shared memory): HBM-bound.  Algorithmic bytes
+            # (MfPlan::bytes_fwd): slot values + lifted rhs read once, every factor panel written once,
+            # every contribution block (lower triangle + rhs rows) written once and read once by its parent.  Time: CUDA
+            # events around the forward launches of every sub-batch, on the library's stream.
+            ms_f, ms_b = st["mf_ms_fwd"], st["mf_ms_bwd"]
+            achieved = st["mf_bytes_fwd"] / (ms_f * 1e-3) / 1e9 if ms_f > 0 else 0.0
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "r02_mf_forward_ncu.json")
+            if os.path.exists(tpath):
+                with open(tpath) as f:
+                    tj = json.load(f)
+                traffic, traffic_src = tj["dram_bytes_per_cell"] * n_total, "profiles/r02_mf_forward_ncu.json: " + tj["capture"]
+            fp64_pk, fp64_src = fp64_peak(dev)
+            roofline = {"bound": "hbm", "kernel": "k_mf_forward", "achieved": achieved, "peak": hbm_pk, "unit": "GB/s",
+                        "frac": achieved / hbm_pk, "traffic": traffic, "traffic_source": traffic_src, "peak_source": hbm_src,
+                        "bytes_per_step": st["mf_bytes_fwd"], "ms_per_step": ms_f,
+                        "backward": {"kernel": "k_mf_backward", "bytes_per_step": st["mf_bytes_bwd"], "ms_per_step": ms_b,
+                                     "achieved": st["mf_bytes_bwd"] / (ms_b * 1e-3) / 1e9 if ms_b > 0 else 0.0},
+                        "launches_per_step": int(st["mf_launches"]),
+                        "step_frac": (st["mf_bytes_fwd"] + st["mf_bytes_bwd"]) / (ms_step * 1e-3) / 1e9 / hbm_pk,
+                        "flops_per_step": st["mf_flops"], "step_fp64_tflops": st["mf_flops"] / (ms_step * 1e-3) / 1e12,
+                        "fp64_peak_tflops": fp64_pk, "fp64_peak_source": fp64_src}
+        elif solver_used == "minres":
             # dominant kernel k_minres_spmm: algorithmic bytes per launch: every per-cell matrix
             # value of the interior system once per iteration + rhs/solution amortised over the iterations.
             launches = max(1, st["krylov_spmm_launches"])
@@ -334,12 +360,12 @@ def main():
                     "timing": "host wall clock around msfec_build_basis (pinned host buffers in, host buffers out), max over ranks"},
             "gpu_launches": int(sum(s["kernel_launches"] for s in stats)),
             "roofline": roofline,
-            "solver": args.solver,
+            "solver": solver_used,
             "phases_ms": {kk: st[kk] for kk in ("ms_assemble", "ms_lift", "ms_solve", "ms_gram")},
             "krylov": {"iterations_max": st["iterations_max"], "iterations_mean": st["iterations_mean"],
                        "residual_max": st["residual_max"], "not_converged": st["not_converged"]},
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             n_sample = args.cpu_sample or 64 * cores
             v, n_done, dt = cpu_oracle_throughput(n_sample, g_ref, L, cores)
             line["cpu_baseline"] = {"value": v, "unit": "coarse cells/s", "cores": cores, "kind": "port",

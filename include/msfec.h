@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MSFEC_ABI_VERSION 1
+#define MSFEC_ABI_VERSION 2
 
 enum msfec_pairing {
   MSFEC_Q      = 0, /* FE_Q(1)                      k = 8   (q_basis.cc:16)        */
@@ -72,8 +72,22 @@ typedef struct msfec_problem {
    * discrete solution needs tighter values).  <= 0 selects defaults. */
   double krylov_rtol;
   int32_t krylov_max_iter;
-  int32_t cells_per_batch;       /* coarse cells resident on the device at once      */
+  int32_t cells_per_batch;       /* coarse cells resident on the device at once; <= 0: derived from free memory */
+  /* Solver of the local problems (enum msfec_solver).  MSFEC_SOLVER_AUTO follows the .prm: "use direct solver
+   * basis = true" asks for the exact solve; "= false" (what every shipped .prm sets) asks for the reference's
+   * iterative tolerance (1e-6), which the exact factorisation satisfies -- so AUTO picks the fastest exact solver that
+   * fits (multifrontal up to 3 local refinements, banded block LDL^T beyond) and falls back to batched MINRES only when
+   * no factorisation plan exists for the problem size. */
+  int32_t solver;
+  int32_t reserved0;
 } msfec_problem;
+
+enum msfec_solver {
+  MSFEC_SOLVER_AUTO = 0,
+  MSFEC_SOLVER_MINRES = 1,       /* batched preconditioned MINRES (solve_iterative, ned_rt_basis.cc:637-847)        */
+  MSFEC_SOLVER_BAND = 2,         /* batched block LDL^T on a layer/plane or dissected band (solve_direct, :579-634)  */
+  MSFEC_SOLVER_MULTIFRONTAL = 3  /* batched multifrontal LDL^T, fronts in shared memory (solve_direct, :579-634)    */
+};
 
 typedef struct msfec_stats {
   int32_t n_cells;
@@ -97,8 +111,15 @@ typedef struct msfec_stats {
   double direct_flops;           /* FP64 tensor-core flops of the build: trailing updates (lower triangle) + solves */
   double direct_flops_timed;     /* flops of the k_direct_update_s launches that were bracketed by events           */
   double direct_ms_update;       /* summed device time of those launches                                            */
-  int32_t solver;                /* 0 = batched MINRES, 1 = batched block LDL^T                       */
+  int32_t solver;                /* 0 = batched MINRES, 1 = batched block LDL^T (band), 2 = batched multifrontal LDL^T */
   int32_t direct_timed_launches; /* number of event-bracketed k_direct_update_s launches                             */
+  /* multifrontal path */
+  double mf_flops;               /* FP64 flops of the front kernels of the build (padded front sizes)                */
+  double mf_bytes_fwd;           /* algorithmic HBM bytes of k_mf_forward: slot values + rhs read, every factor panel
+                                  * written once, every contribution block written once and read once    */
+  double mf_bytes_bwd;           /* ... of k_mf_backward: factor panels read once, solution gathered / written        */
+  double mf_ms_fwd, mf_ms_bwd;   /* summed device time of the k_mf_forward / k_mf_backward launches (CUDA events)     */
+  int64_t mf_launches;           /* k_mf_forward + k_mf_backward launches of the build                               */
 } msfec_stats;
 
 typedef struct msfec_ctx msfec_ctx;

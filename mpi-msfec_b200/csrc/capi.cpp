@@ -9,6 +9,7 @@
 
 #include "../../include/msfec.h"
 #include "engine.h"
+#include "mfplan.h"
 #include "prm.h"
 #include "topology.h"
 
@@ -18,6 +19,7 @@ struct msfec_ctx {
   ProblemSpec spec;
   Topology topo;
   DirectPlan plan;
+  MfPlan mf;
   Engine *engine = nullptr;
   std::string last_error;
 };
@@ -232,7 +234,10 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
       if (!have && p->use_direct_solver_basis) throw std::runtime_error(why);
       ctx->plan = have ? std::move(plan) : DirectPlan();
     }
-    if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan);
+    // multifrontal plan (fronts resident in shared memory): feasible up to 3 local refinements; the engine prefers it
+    try { ctx->mf = build_mf_plan(ctx->topo); }
+    catch (const std::exception &ex) { ctx->mf = MfPlan(); ctx->mf.why = ex.what(); }
+    if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan, ctx->mf);
     *out = ctx;
     return MSFEC_OK;
   } catch (const std::invalid_argument &e) {
@@ -363,7 +368,29 @@ int msfec_debug_table(const msfec_ctx *ctx, const char *name, void *out, size_t 
       else if (n == pre + ".val") dv = &nops[i].val;
     }
   }
+  const MfPlan &mf = ctx->mf;
+  std::vector<int32_t> mf_flat;
+  if (n == "mf.fronts") {
+    for (auto &F : mf.fronts) { const int32_t *q = reinterpret_cast<const int32_t *>(&F); mf_flat.insert(mf_flat.end(), q, q + kMfFrontFields); }
+    iv = &mf_flat;
+  } else if (n == "mf.children") {
+    for (auto &c : mf.children) { mf_flat.push_back(c.front); mf_flat.push_back(c.n_own); mf_flat.push_back(c.cmap_off); mf_flat.push_back(c.pinv_off); }
+    iv = &mf_flat;
+  }
+  else if (n == "mf.front_idx") iv = &mf.front_idx; else if (n == "mf.own_rows") iv = &mf.own_rows;
+  else if (n == "mf.cmap") iv = &mf.cmap; else if (n == "mf.pinv") iv = &mf.pinv;
+  else if (n == "mf.pe_dest") iv = &mf.pe_dest; else if (n == "mf.pe_ref") iv = &mf.pe_ref;
+  else if (n == "mf.ps_dest") iv = &mf.ps_dest; else if (n == "mf.ps_val") dv = &mf.ps_val;
+  else if (n == "mf.pc_dest") iv = &mf.pc_dest; else if (n == "mf.pc_val") dv = &mf.pc_val;
+  else if (n == "mf.perm") iv = &mf.perm; else if (n == "mf.inv_perm") iv = &mf.inv_perm;
+  else if (n == "mf.level_off") iv = &mf.level_off; else if (n == "mf.level_fronts") iv = &mf.level_fronts;
+  else if (n == "mf.smem_fwd") iv = &mf.smem_fwd; else if (n == "mf.smem_bwd") iv = &mf.smem_bwd;
   std::vector<double> plan_info;
+  if (n == "mf.info") {
+    plan_info = {mf.feasible ? 1.0 : 0.0, (double)mf.kr, (double)mf.NP, (double)mf.n_levels, (double)mf.l_doubles,
+                 (double)mf.c_doubles, mf.flops, mf.bytes_fwd + mf.bytes_bwd, (double)mf.pinned_row, (double)kMfFrontFields};
+    dv = &plan_info;
+  }
   if (n == "direct.info") { plan_info = {dp.update_flops, (double)dp.band_doubles, (double)dp.n_slabs, (double)dp.NP}; dv = &plan_info; }
   if (n == "G") dv = &t.G; else if (n == "F1") dv = &t.F1;
   else if (n == "diag_slot0") iv = &t.diag_slot0; else if (n == "diag_slot1") iv = &t.diag_slot1;

@@ -7,6 +7,7 @@
 
 #include "../../include/msfec.h"
 #include "expr.h"
+#include "mfplan.h"
 #include "topology.h"
 
 namespace msfec {
@@ -37,7 +38,7 @@ struct ProblemSpec {          // owned copy of msfec_problem with strings resolv
 class Engine;   // defined in engine.cu
 
 // Factory; throws std::runtime_error.  device >= 0.
-Engine *engine_create(int device, const ProblemSpec &spec, const Topology &topo, const DirectPlan &plan);
+Engine *engine_create(int device, const ProblemSpec &spec, const Topology &topo, const DirectPlan &plan, const MfPlan &mf);
 void engine_destroy(Engine *e);
 int engine_build(Engine *e, int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix,
                  double *elem_rhs, bool device_ptrs, msfec_stats *stats, std::string &err);

@@ -18,6 +18,8 @@ import os
 import numpy as np
 
 PAIRING = {"Q": 0, "Q_NED": 1, "NED_RT": 2, "RT_DQ": 3}
+SOLVER = {"auto": 0, "minres": 1, "band": 2, "mf": 3}          # enum msfec_solver
+SOLVER_STAT = {"minres": 0, "band": 1, "mf": 2}               # msfec_stats.solver
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmsfec_b200.so")
 
@@ -38,6 +40,7 @@ class Problem(C.Structure):
         ("b_expression", C.c_char_p), ("rhs_expression", C.c_char_p), ("rhs_constants", C.c_char_p),
         ("random_field_seed", C.c_uint64), ("random_field_sigma", C.c_double),
         ("krylov_rtol", C.c_double), ("krylov_max_iter", C.c_int32), ("cells_per_batch", C.c_int32),
+        ("solver", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -51,6 +54,8 @@ class Stats(C.Structure):
         ("krylov_spmm_launches", C.c_int64),
         ("direct_update_launches", C.c_int64), ("direct_flops", C.c_double), ("direct_flops_timed", C.c_double),
         ("direct_ms_update", C.c_double), ("solver", C.c_int32), ("direct_timed_launches", C.c_int32),
+        ("mf_flops", C.c_double), ("mf_bytes_fwd", C.c_double), ("mf_bytes_bwd", C.c_double), ("mf_ms_fwd", C.c_double),
+        ("mf_ms_bwd", C.c_double), ("mf_launches", C.c_int64),
     ]
 
     def as_dict(self):

@@ -148,3 +148,123 @@ def emulate_direct(bb, vals, kscale, b):
     real = inv >= 0
     x[inv[real]] = xp[real]
     return x, d, inv
+
+
+MF_FIELDS = ["s", "s8", "u", "u8", "m", "ldx", "level", "parent", "own_base", "idx_off", "row_off", "pe_lo", "pe_hi",
+             "ps_lo", "ps_hi", "pc_lo", "pc_hi", "ch_lo", "ch_hi", "l_off", "c_off", "n_rows_real"]
+
+
+def mf_tables(bb):
+    info = bb.table("mf.info")
+    nfld = int(info[9])
+    assert nfld == len(MF_FIELDS)
+    fr = bb.table("mf.fronts").reshape(-1, nfld)
+    T = dict(info=dict(feasible=bool(info[0]), kr=int(info[1]), NP=int(info[2]), n_levels=int(info[3]),
+                       l_doubles=int(info[4]), c_doubles=int(info[5]), flops=info[6], bytes=info[7], pinned_row=int(info[8])),
+             fronts=[dict(zip(MF_FIELDS, row.tolist())) for row in fr],
+             children=bb.table("mf.children").reshape(-1, 4))
+    for name in ("front_idx", "own_rows", "cmap", "pinv", "pe_dest", "pe_ref", "ps_dest", "ps_val", "pc_dest", "pc_val",
+                 "perm", "inv_perm", "level_off", "level_fronts", "smem_fwd", "smem_bwd"):
+        T[name] = bb.table("mf." + name)
+    return T
+
+
+def emulate_multifrontal(bb, vals, kscale, b):
+    """numpy model of the multifrontal kernels (csrc/mf.cuh) driven by the library's MfPlan tables: level by level,
+    every front assembles its panel [m x s8] from the per-cell slot values, the shared entries, the rhs and the first
+    n_own columns of its children's contribution blocks; factors it (LDL^T without pivoting, X = L D kept for the
+    rows below); stores the factor panel; forms its contribution block C (column-major (u8+kr) x u8) by gathering the
+    children through `pinv` and subtracting X L21^T.  Backward pass top-down through front_idx.  Returns
+    (x in interior numbering, pivots d in padded numbering, padded->interior map)."""
+    T = mf_tables(bb)
+    assert T["info"]["feasible"]
+    kr, NP = T["info"]["kr"], T["info"]["NP"]
+    k = b.shape[1]
+    Lst = np.zeros(T["info"]["l_doubles"]); Cst = np.full(T["info"]["c_doubles"], np.nan)
+    dall = np.ones(NP)
+    fronts, ch = T["fronts"], T["children"]
+    order_fwd = [f for l in range(T["info"]["n_levels"]) for f in T["level_fronts"][T["level_off"][l]:T["level_off"][l + 1]]]
+    for f in order_fwd:
+        F = fronts[f]
+        s8, u8, m, ldx = F["s8"], F["u8"], F["m"], F["ldx"]
+        P = np.zeros(m * ldx)
+        sl = slice(F["pe_lo"], F["pe_hi"]); ref = T["pe_ref"][sl]
+        P[T["pe_dest"][sl]] = np.where(ref & 1, -1.0, 1.0) * vals[ref >> 1]
+        sl = slice(F["ps_lo"], F["ps_hi"]); P[T["ps_dest"][sl]] = T["ps_val"][sl] * kscale
+        sl = slice(F["pc_lo"], F["pc_hi"]); P[T["pc_dest"][sl]] = T["pc_val"][sl]
+        P = P.reshape(m, ldx)
+        rows = T["own_rows"][F["row_off"]:F["row_off"] + s8]
+        for c in range(s8):
+            if rows[c] >= 0:
+                P[s8 + u8:s8 + u8 + k, c] = b[rows[c]]
+        kids = ch[F["ch_lo"]:F["ch_hi"]]
+        for (cf, n_own, cmap_off, pinv_off) in kids:
+            Cf = fronts[cf]
+            ldc = Cf["u8"] + kr
+            Cc = Cst[Cf["c_off"]:Cf["c_off"] + ldc * Cf["u8"]].reshape(Cf["u8"], ldc)      # [col][row]
+            cmap = T["cmap"][cmap_off:cmap_off + ldc]
+            for j in range(n_own):
+                assert 0 <= cmap[j] < s8
+                for i in range(j, ldc):
+                    if cmap[i] >= 0:
+                        P[cmap[i], cmap[j]] += Cc[j, i]
+        # factor the panel: right-looking LDL^T; afterwards the own block holds the unit-lower L (strictly lower part),
+        # the rows below hold X = L D
+        X = P[:, :s8].copy()
+        d = np.zeros(s8)
+        for j in range(s8):
+            d[j] = X[j, j]
+            lcol_own = X[j + 1:s8, j] / d[j]                       # L(i, j) for own rows i > j
+            X[j + 1:, j + 1:s8] -= np.outer(X[j + 1:, j], lcol_own)
+            X[j + 1:s8, j] = lcol_own
+        Lfull = X.copy()
+        Lfull[s8:, :] = X[s8:, :] / d[None, :]
+        out = Lfull.copy()
+        out[np.arange(s8), np.arange(s8)] = d
+        Lst[F["l_off"]:F["l_off"] + m * s8] = out.reshape(-1)
+        dall[F["own_base"]:F["own_base"] + s8] = d
+        # contribution block
+        if u8:
+            ldc = u8 + kr
+            Cn = np.zeros((u8, ldc))
+            for (cf, n_own, cmap_off, pinv_off) in kids:
+                Cf = fronts[cf]
+                ldcc = Cf["u8"] + kr
+                Cc = Cst[Cf["c_off"]:Cf["c_off"] + ldcc * Cf["u8"]].reshape(Cf["u8"], ldcc)
+                pinv = T["pinv"][pinv_off:pinv_off + m]
+                for j in range(u8):
+                    jc = pinv[s8 + j]
+                    if jc < 0:
+                        continue
+                    for i in range(j, ldc):
+                        ic = pinv[s8 + i]
+                        if ic >= 0:
+                            assert ic >= jc
+                            Cn[j, i] += Cc[jc, ic]
+            Xb = X[s8:, :]                       # (u8 + kr) x s8
+            Lb = Lfull[s8:s8 + u8, :]            # u8 x s8
+            Cn -= (Xb @ Lb.T).T
+            for j in range(u8):
+                Cn[j, :j] = np.nan               # entries above the diagonal are never written by the kernel
+            Cst[F["c_off"]:F["c_off"] + ldc * u8] = Cn.reshape(-1)
+    # backward
+    xp = np.zeros((NP, kr))
+    for f in reversed(order_fwd):
+        F = fronts[f]
+        s8, u8, m = F["s8"], F["u8"], F["m"]
+        Lp = Lst[F["l_off"]:F["l_off"] + m * s8].reshape(m, s8)
+        idx = T["front_idx"][F["idx_off"]:F["idx_off"] + s8 + u8]
+        xu = np.zeros((u8, kr))
+        for r in range(u8):
+            if idx[s8 + r] >= 0:
+                xu[r] = xp[idx[s8 + r]]
+        t = Lp[s8 + u8:, :].T.copy()             # z: s8 x kr
+        t -= Lp[s8:s8 + u8, :].T @ xu
+        L11 = np.tril(Lp[:s8, :], -1) + np.eye(s8)
+        xo = np.linalg.solve(L11.T, t)
+        xp[F["own_base"]:F["own_base"] + s8] = xo
+    inv = T["inv_perm"]
+    x = np.zeros_like(b)
+    real = inv >= 0
+    x[inv[real]] = xp[real][:, :k]
+    return x, dall, inv

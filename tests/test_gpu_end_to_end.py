@@ -12,9 +12,9 @@ from oracle import msfec_oracle as mo
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("direct", [1, 0], ids=["direct", "minres"])
+@pytest.mark.parametrize("solver", ["mf", "band", "minres"])
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
-def test_final_multiscale_solution_matches_oracle(msfec, pairing, direct):
+def test_final_multiscale_solution_matches_oracle(msfec, pairing, solver):
     g_ref, L = 2, 2
     cells = mo.morton_cells(g_ref)
     ids = np.arange(len(cells))
@@ -27,7 +27,7 @@ def test_final_multiscale_solution_matches_oracle(msfec, pairing, direct):
         kw_o = dict(rhs_expr=rhs03, rhs_constants={"alpha": 100.0, "beta": 10.0})
         kw_l = dict(rhs_expression=rhs03.encode(), rhs_constants=b"alpha=100, beta=10")
     prob = oracle_problem(pairing, L, **kw_o)
-    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, use_direct_solver_basis=direct, **kw_l), device=0).run(cells, ids)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, solver=msfec.SOLVER[solver], **kw_l), device=0).run(cells, ids)
     # oracle side
     Mo, ro, X0o, X1o = [], [], [], []
     for c in ids:
@@ -62,7 +62,7 @@ def test_final_multiscale_solution_matches_oracle(msfec, pairing, direct):
             assert rel_err(u_g, u_o) < 1e-8
     for name in norms:
         rel = np.sqrt(num[name] / max(den[name], 1e-300))
-        print(pairing, "direct" if direct else "minres", name, "relative difference", rel)
+        print(pairing, solver, name, "relative difference", rel)
         assert rel < 1e-8, (name, rel)
 
 

@@ -22,20 +22,34 @@ def _check_cells(bb, prob, cells, ids, which):
     return worst
 
 
-@pytest.mark.parametrize("direct", [0, 1], ids=["minres", "direct"])
+SOLVERS = ["minres", "band", "mf"]
+
+
+@pytest.mark.parametrize("solver", SOLVERS)
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
 @pytest.mark.parametrize("L", [2, 3])
-def test_prm_coefficients_match_oracle(msfec, pairing, L, direct):
-    """configs[0..3] coefficients (examples/prm == reference test-01 files) on the 64-cell coarse mesh,
-    through both solver paths of the reference: `use direct solver basis` false (batched MINRES) / true
-    (batched block LDL^T)."""
+def test_prm_coefficients_match_oracle(msfec, pairing, L, solver):
+    """configs[0..3] coefficients (examples/prm == reference test-01 files) on the 64-cell coarse mesh, through all
+    three solvers of the local problems: batched MINRES (the reference's solve_iterative), banded block LDL^T and
+    multifrontal LDL^T (the reference's solve_direct)."""
     cells = mo.morton_cells(2)
     ids = np.arange(64)
-    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, use_direct_solver_basis=direct), device=0).run(cells, ids)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, solver=msfec.SOLVER[solver]), device=0).run(cells, ids)
     worst = _check_cells(bb, oracle_problem(pairing, L), cells, ids, (0, 21, 37, 63))
     print(pairing, L, "worst", worst, bb.stats)
     assert worst < TOL
-    assert bb.stats["not_converged"] == 0 and bb.stats["kernel_launches"] > 0 and bb.stats["solver"] == direct
+    assert bb.stats["not_converged"] == 0 and bb.stats["kernel_launches"] > 0
+    assert bb.stats["solver"] == msfec.SOLVER_STAT[solver]
+
+
+@pytest.mark.parametrize("flag", [0, 1])
+def test_auto_solver_selection(msfec, flag):
+    """`use direct solver basis` true and false (what every shipped .prm sets) both get an exact factorisation: the
+    multifrontal solver up to 3 local refinements; the flag alone never routes to the slow MINRES fallback."""
+    cells = mo.morton_cells(2)
+    bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 3, use_direct_solver_basis=flag), device=0).run(cells, np.arange(64))
+    assert bb.stats["solver"] == msfec.SOLVER_STAT["mf"] and bb.stats["residual_max"] < 1e-11
+    assert bb.stats["mf_launches"] > 0 and bb.stats["mf_ms_fwd"] > 0 and bb.stats["mf_ms_bwd"] > 0
 
 
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
@@ -49,12 +63,12 @@ def test_golden_fixtures(msfec, pairing):
         assert np.abs(bb.get_global_element_rhs()[c] - ro).max() <= TOL * max(np.abs(ro).max(), 1e-300)
 
 
-@pytest.mark.parametrize("direct", [0, 1], ids=["minres", "direct"])
-def test_random_field_ragged_batches(msfec, direct):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_random_field_ragged_batches(msfec, solver):
     """C5-style rough field; 70 cells = 2 full lane groups + a ragged one, split over 2 batches."""
     cells = mo.morton_cells(3)[100:170]
     ids = np.arange(100, 170)
-    p = lib_problem(msfec, "NED_RT", 2, random_seed=20261017, cells_per_batch=64, use_direct_solver_basis=direct)
+    p = lib_problem(msfec, "NED_RT", 2, random_seed=20261017, cells_per_batch=64, solver=msfec.SOLVER[solver])
     bb = msfec.BasisBuilder(p, device=0).run(cells, ids)
     worst = _check_cells(bb, oracle_problem("NED_RT", 2, random_seed=20261017), cells, ids, (0, 31, 32, 63, 64, 69))
     assert worst < TOL
@@ -101,11 +115,11 @@ def test_constant_coefficient_reproduction_on_gpu(msfec):
             assert rel_err(bb.get_global_element_matrix()[c], M0) < TOL
 
 
-@pytest.mark.parametrize("direct", [0, 1], ids=["minres", "direct"])
-def test_structure_properties_at_scale(msfec, direct):
+@pytest.mark.parametrize("solver", SOLVERS)
+def test_structure_properties_at_scale(msfec, solver):
     """Size-independent properties on 1024 random-field cells (no oracle solve needed)."""
     cells = mo.morton_cells(4)[:1024]
-    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017, use_direct_solver_basis=direct)
+    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017, solver=msfec.SOLVER[solver])
     bb = msfec.BasisBuilder(p, device=0).run(cells)
     M = bb.get_global_element_matrix()
     s = np.abs(M).max(axis=(1, 2))
@@ -126,11 +140,12 @@ def test_full_size_c5_properties(msfec):
     same cell solved in a job of its own and in a ragged 33-cell job) and three cells against the oracle."""
     cells = mo.morton_cells(5)
     assert len(cells) == 32768
-    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017, use_direct_solver_basis=1)
+    p = lib_problem(msfec, "NED_RT", 3, random_seed=20261017)               # solver: auto -> multifrontal
     ids = np.arange(32768)
     bb = msfec.BasisBuilder(p, device=0).run(cells, cell_ids=ids)
     M = bb.get_global_element_matrix().copy(); r = bb.get_global_element_rhs().copy()
     st = dict(bb.stats)
+    assert st["solver"] == msfec.SOLVER_STAT["mf"]
     assert st["not_converged"] == 0 and st["residual_max"] < 1e-11          # true residual of every cell
     s = np.abs(M).max(axis=(1, 2))
     assert np.isfinite(M).all() and np.isfinite(r).all() and (s > 0).all()
@@ -146,9 +161,17 @@ def test_full_size_c5_properties(msfec):
         assert np.abs(M2 - M[sel]).max() <= 1e-11 * s[sel].max()
         bb2.close()
     prob = oracle_problem("NED_RT", 3, random_seed=20261017)
-    for c in (0, 12345, 32767):
+    # 64 cells stratified over the Morton range (one per 512-cell stratum, pseudo-random offset) against the oracle
+    rng = np.random.default_rng(5)
+    sample = [0, 32767] + [int(512 * i + rng.integers(512)) for i in range(1, 63)]
+    for c in sample:
         Mo, ro, *_ = mo.build_basis(prob, cells[c], c)
-        assert rel_err(M[c], Mo) < TOL and np.abs(r[c] - ro).max() <= TOL * max(np.abs(ro).max(), 1e-300)
+        assert rel_err(M[c], Mo) < TOL and np.abs(r[c] - ro).max() <= TOL * max(np.abs(ro).max(), 1e-300), c
+    # the banded solver on one stratum gives the same matrices (two independent factorisations)
+    sel = np.arange(8192, 8192 + 256)
+    bb3 = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 3, random_seed=20261017, solver=msfec.SOLVER["band"]), device=0).run(cells[sel], ids[sel])
+    assert np.abs(bb3.get_global_element_matrix() - M[sel]).max() <= 1e-10 * s[sel].max()
+    bb3.close()
     bb.close()
 
 
@@ -223,14 +246,15 @@ def test_cpp_host_driver(msfec, tmp_path):
 
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
 def test_reference_prm_configs_full_size(msfec, pairing):
-    """BASELINE configs[0..3] at their real size: the reference's prm_*_test-01.prm (64 coarse cells,
-    4 local refinements, n = 16) through the direct path; two cells against the oracle, structure on all."""
+    """BASELINE configs[0..3] at their real size and VERBATIM: the reference's prm_*_test-01.prm (64 coarse cells,
+    4 local refinements, n = 16, `use direct solver basis = false` as shipped) with no override; the automatic solver
+    selection takes the banded block LDL^T there.  Two cells against the oracle, structure on all."""
     cells = mo.morton_cells(2)
     p = msfec.problem_from_prm(os.path.join(ROOT, "examples", "prm", {"Q": "prm_q_test-01.prm", "Q_NED": "prm_q_ned_test-01.prm",
                                "NED_RT": "prm_ned_rt_test-01.prm", "RT_DQ": "prm_rt_dq_test-01.prm"}[pairing]), pairing)
-    assert p.n_refine_local == 4
-    p.use_direct_solver_basis = 1
+    assert p.n_refine_local == 4 and p.use_direct_solver_basis == 0 and p.solver == 0
     bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(64))
+    assert bb.stats["solver"] == msfec.SOLVER_STAT["band"] and bb.stats["not_converged"] == 0 and bb.stats["residual_max"] < 1e-10
     M = bb.get_global_element_matrix()
     assert np.isfinite(M).all()
     k0 = {"Q": 8, "Q_NED": 8, "NED_RT": 12, "RT_DQ": 6}[pairing]
@@ -243,9 +267,10 @@ def test_reference_prm_configs_full_size(msfec, pairing):
 
 @pytest.mark.parametrize("pairing", ["Q", "RT_DQ"])
 def test_minres_full_size(msfec, pairing):
-    """The iterative path ('use direct solver basis = false', as shipped in the reference .prm) at n = 16."""
+    """The batched MINRES path (msfec_problem.solver = MSFEC_SOLVER_MINRES; the memory fallback of the automatic selection)
+    at n = 16."""
     cells = mo.morton_cells(2)[:32]
-    p = lib_problem(msfec, pairing, 4)
+    p = lib_problem(msfec, pairing, 4, solver=msfec.SOLVER["minres"])
     bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(32))
     worst = _check_cells(bb, oracle_problem(pairing, 4), cells, np.arange(32), (5,))
     print(pairing, "L=4 minres worst", worst, bb.stats["iterations_max"])

@@ -22,13 +22,26 @@ def test_library_exports_every_declared_symbol(msfec):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/msfec.h but not exported"
     assert set(msfec.EXPORTS) == declared
-    assert lib.msfec_abi_version() == 1
+    assert lib.msfec_abi_version() == 2
 
 
 def test_struct_layout_matches_header(msfec):
     # sizeof checks guard the ctypes mirror against drift
-    assert C.sizeof(msfec.Problem) == 4 * 6 + 4 * 3 + 4 + 8 * 3 * 2 + 8 * 2 + 8 * 3 + 8 + 8 + 8 + 4 + 4
-    assert C.sizeof(msfec.Stats) == 4 * 8 + 8 * 9 + 8 + 8 + 8 * 3 + 4 + 4
+    assert C.sizeof(msfec.Problem) == 4 * 6 + 4 * 3 + 4 + 8 * 3 * 2 + 8 * 2 + 8 * 3 + 8 + 8 + 8 + 4 + 4 + 4 + 4
+    assert C.sizeof(msfec.Stats) == 4 * 8 + 8 * 9 + 8 + 8 + 8 * 3 + 4 + 4 + 8 * 5 + 8
+    # field order of the ctypes mirrors == declaration order in include/msfec.h
+    hdr = open(os.path.join(ROOT, "include", "msfec.h")).read()
+    for name, cls in (("msfec_problem", msfec.Problem), ("msfec_stats", msfec.Stats)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        decl = []
+        for stmt in body.split(";"):
+            stmt = stmt.strip()
+            if not stmt:
+                continue
+            names = re.sub(r"^(const\s+)?\w+\s+\*?", "", stmt)
+            decl += [re.sub(r"\[.*?\]|\*|\s", "", x) for x in names.split(",")]
+        assert decl == [f for f, _ in cls._fields_], (name, decl)
 
 
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
@@ -219,3 +232,47 @@ def test_direct_plan_nested_dissection(msfec, monkeypatch, pairing, n_blocks, n_
         assert int(bb2.table("direct.info")[3]) == 2656          # layers/planes stay the default at n = 8
     bb4 = msfec.BasisBuilder(lib_problem(msfec, pairing, 4), device=-1)
     assert int(bb4.table("direct.info")[2]) == 132               # nested dissection chosen at n = 16 (127 + 3 + 2 pieces)
+
+
+@pytest.mark.parametrize("pairing,L,seed", [("Q", 2, 0), ("Q_NED", 2, 0), ("NED_RT", 2, 0), ("RT_DQ", 2, 0), ("NED_RT", 1, 0), ("RT_DQ", 1, 0),
+                                             ("Q", 3, 0), ("Q_NED", 3, 0), ("RT_DQ", 3, 0), ("NED_RT", 3, 20261017)])
+def test_multifrontal_plan_tables(msfec, pairing, L, seed):
+    """The multifrontal plan (csrc/mfplan.cpp: nested dissection to 2^3-cell boxes, supernodes, fronts, index maps,
+    assembly lists) replayed in numpy front by front exactly as k_mf_forward / k_mf_backward walk it: the no-pivot
+    LDL^T reproduces the sparse-LU solution, pivots are positive on sigma-type and negative on u-type unknowns, every
+    front fits one SM's shared memory."""
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L, random_seed=seed), device=-1)
+    T = emulate.mf_tables(bb)
+    assert T["info"]["feasible"]
+    assert max(T["smem_fwd"]) <= 227 * 1024 and max(T["smem_bwd"]) <= 227 * 1024
+    cells = mo.morton_cells(2)
+    prob = oracle_problem(pairing, L, random_seed=seed)
+    M, r, Z, dbg = emulate.emulate_cell(bb, prob, cells[37], 37)
+    D = emulate.dims_of(bb)
+    h = (cells[37][7][0] - cells[37][0][0]) / D["n"]
+    x, d, inv = emulate.emulate_multifrontal(bb, dbg["vals"], h ** D["k_h_exponent"], dbg["b"])
+    ref = dbg["x"]
+    sel = np.arange(D["NI0"]) if pairing == "RT_DQ" else np.arange(D["NI"])     # RT_DQ: u is fixed up to a constant
+    assert np.abs(x[sel] - ref[sel]).max() <= 1e-9 * np.abs(ref[sel]).max()
+    real = inv >= 0
+    is_u = np.zeros(len(inv), bool); is_u[real] = inv[real] >= D["NI0"]
+    assert (d[real & ~is_u] > 0).all() and (d[real & is_u] < 0).all()
+    assert (d[~real] == -1.0).sum() == (1 if pairing == "RT_DQ" else 0) and np.isin(d[~real], (1.0, -1.0)).all()
+    # structure: children precede parents, a parent sits above its children, own columns of the children lead
+    fr = T["fronts"]
+    for f, F in enumerate(fr):
+        assert F["s8"] % 8 == 0 and F["u8"] % 8 == 0 and F["m"] == F["s8"] + F["u8"] + T["info"]["kr"]
+        assert F["ldx"] % 16 in (4, 12) and F["ldx"] >= F["s8"]
+        if F["parent"] >= 0:
+            assert F["parent"] > f and fr[F["parent"]]["level"] > F["level"]
+    if L == 3 and pairing == "NED_RT":
+        # C5: 34 MFLOP of exact elimination per cell (the 32-padded layer/plane band executes 420)
+        assert T["info"]["flops"] < 80e6 and (T["info"]["l_doubles"] + T["info"]["c_doubles"]) * 8 < 10e6
+
+
+def test_multifrontal_plan_limits(msfec):
+    """From 4 local refinements on the fronts of the top separators outgrow shared memory: the plan splits them into chains
+    (or reports infeasible) and the engine keeps the banded solver there."""
+    bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 4), device=-1)
+    info = emulate.mf_tables(bb)["info"]
+    assert (info["l_doubles"] + info["c_doubles"]) * 8 > (64 << 20) or not info["feasible"]
