@@ -1231,8 +1231,9 @@ void Engine::upload_mf() {
   int max_f = 0, max_b = 0;
   for (int v : MF_.smem_fwd) max_f = std::max(max_f, v);
   for (int v : MF_.smem_bwd) max_b = std::max(max_b, v);
-  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
-  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
+  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
+  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
+  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
   for (auto &ev : ev_mf_) CUDA_OK(cudaEventCreate(&ev));
 }
@@ -1273,12 +1274,17 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
     for (int l = 0; l < MF_.n_levels; ++l) {
       const int nfl = MF_.level_off[l + 1] - MF_.level_off[l];
       const size_t sm = (size_t)MF_.smem_fwd[l];
+      // threads per front by its shared-memory footprint: small fronts share an SM (6 CTAs of 4 warps), fronts that own an SM
+      // get 16 warps to hide the latency of the children gathers
       if (sm <= 56 * 1024)
-        k_mf_forward<128><<<dim3(nfl, nc), 128, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
-                                                              d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
+        k_mf_forward<128, 6><<<dim3(nfl, nc), 128, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
+                                                                 d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
+      else if (sm <= 112 * 1024)
+        k_mf_forward<256, 2><<<dim3(nfl, nc), 256, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
+                                                                 d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
       else
-        k_mf_forward<256><<<dim3(nfl, nc), 256, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
-                                                              d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
+        k_mf_forward<512, 1><<<dim3(nfl, nc), 512, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
+                                                                 d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
     }
     CUDA_OK(cudaEventRecord(mf_marks_[mf_marks_used_ + 1], stream_));
     for (int l = MF_.n_levels - 1; l >= 0; --l) {

@@ -35,13 +35,18 @@ constexpr int kMfMaxChildren = 8;
 __host__ __device__ inline size_t mf_fwd_smem_bytes(int m, int ldx, int s8, int nch) {
   return ((size_t)m * ldx + 2 * (size_t)s8 + 8 * (size_t)s8) * sizeof(double) + (size_t)nch * m * sizeof(int);
 }
+// rows of L21 staged at once by k_mf_backward: the whole block when it is small, else ~48 KB worth (multiple of 8)
+__host__ __device__ inline int mf_bwd_chunk(int s8, int u8) {
+  const int cap = (6144 / s8) & ~7;
+  return u8 < cap ? u8 : (cap < 8 ? 8 : cap);
+}
 __host__ __device__ inline size_t mf_bwd_smem_bytes(int s8, int u8, int kr) {
-  return ((size_t)s8 * s8 + (size_t)s8 * kr + (size_t)u8 * kr) * sizeof(double);
+  return ((size_t)s8 * s8 + (size_t)s8 * kr + (size_t)u8 * kr + (size_t)mf_bwd_chunk(s8, u8) * s8) * sizeof(double);
 }
 
 // grid (fronts of the level, cells of the sub-batch), block NT
-template <int NT>
-__global__ void __launch_bounds__(NT)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, double kscale,
              const double *__restrict__ b, int NI, int k, int cell_lo, double *__restrict__ Lst, size_t l_stride,
              double *__restrict__ Cst, size_t c_stride, int *__restrict__ bad) {
@@ -62,7 +67,11 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   int *pinv_s = reinterpret_cast<int *>(Ld + 8 * (size_t)s8);   // [nch][m]
 
   // ---- assemble the panel --------------------------------------------------------------------------------
-  for (int i = tid; i < m * ldx; i += NT) P[i] = 0.0;
+  {
+    double2 *P2 = reinterpret_cast<double2 *>(P);
+    const int n2 = (m * ldx) >> 1;
+    for (int i = tid; i < n2; i += NT) P2[i] = make_double2(0.0, 0.0);
+  }
   __syncthreads();
   {
     const double *vc = vals + (size_t)g * n_slots * kLanes + ln;
@@ -73,10 +82,10 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     }
     for (int e = F.pc_lo + tid; e < F.pc_hi; e += NT) P[M.pc_dest[e]] = M.pc_val[e];
     const double *bc = b + (size_t)g * NI * k * kLanes + ln;
-    for (int idx = tid; idx < s8 * k; idx += NT) {
-      const int c = idx / k, j = idx - c * k;
+    for (int c = warp; c < s8; c += NW) {
       const int row = M.own_rows[F.row_off + c];
-      if (row >= 0) P[(size_t)(s8 + u8 + j) * ldx + c] = bc[((size_t)row * k + j) * kLanes];
+      if (row < 0) continue;
+      for (int j = lane; j < k; j += 32) P[(size_t)(s8 + u8 + j) * ldx + c] = bc[((size_t)row * k + j) * kLanes];
     }
   }
   __syncthreads();
@@ -91,13 +100,15 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     const double *Cc = Cst + (size_t)cell * c_stride + ccoff;
     const int *cmap = M.cmap + ch.cmap_off;
     for (int i = tid; i < m; i += NT) pinv_s[ci * m + i] = M.pinv[ch.pinv_off + i];
-    const int tot = ch.n_own * ldc;
-    for (int idx = tid; idx < tot; idx += NT) {
-      const int j = idx / ldc, i = idx - j * ldc;
-      if (i < j) continue;
-      const int ri = cmap[i];
-      if (ri < 0) continue;
-      P[(size_t)ri * ldx + cmap[j]] += Cc[(size_t)j * ldc + i];
+    for (int j = warp; j < ch.n_own; j += NW) {
+      const int cj = cmap[j];
+      const double *col = Cc + (size_t)j * ldc;
+#pragma unroll 4
+      for (int i = j + lane; i < ldc; i += 32) {
+        const int ri = cmap[i];
+        const double v = col[i];
+        if (ri >= 0) P[(size_t)ri * ldx + cj] += v;
+      }
     }
     __syncthreads();
   }
@@ -107,61 +118,77 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   for (int q = 0; q < S; ++q) {
     const int c0 = q * 8;
     if (q > 0) {
-      // left-looking update of tile column q:  P(R, q) -= X(R, 0:c0) L(q, 0:c0)^T   (L = X D^-1)
-      // MMA m = column inside the tile, n = row inside the tile, k = earlier columns
+      // left-looking update of tile column q:  P(R, q) -= X(R, 0:c0) L(q, 0:c0)^T   (L = X D^-1), four row tiles of a
+      // warp at a time (independent accumulator chains).  MMA m = column inside the tile, n = row, k = earlier columns
       const double *Arow = P + (size_t)(c0 + fr) * ldx + fk;
-      for (int R = q + warp; R < MT; R += NW) {
-        double *t0 = P + (size_t)(R * 8 + 2 * fk) * ldx + c0 + fr;
-        double a0 = t0[0], a1 = t0[ldx];
-        const double *Brow = P + (size_t)(R * 8 + fr) * ldx + fk;
-#pragma unroll 2
-        for (int t = 0; t < c0; t += 4) dmma_m8n8k4(a0, a1, -Arow[t] * dinv[t + fk], Brow[t]);
-        t0[0] = a0; t0[ldx] = a1;
+      for (int R0 = q + warp; R0 < MT; R0 += 4 * NW) {
+        double acc[4][2];
+        double *tp[4];
+        const double *Brow[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int R = min(R0 + u * NW, MT - 1);
+          tp[u] = P + (size_t)(R * 8 + 2 * fk) * ldx + c0 + fr;
+          Brow[u] = P + (size_t)(R * 8 + fr) * ldx + fk;
+          acc[u][0] = tp[u][0]; acc[u][1] = tp[u][ldx];
+        }
+        for (int t = 0; t < c0; t += 4) {
+          const double a = -Arow[t] * dinv[t + fk];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (R0 + u * NW < MT) { tp[u][0] = acc[u][0]; tp[u][ldx] = acc[u][1]; }
       }
       __syncthreads();
     }
-    // LDL^T of the pivot tile, lane (i = lane & 7) = row; every warp computes it (registers + shuffles)
-    const int i = lane & 7;
-    double a[8], dl[8];
+    // LDL^T of the pivot tile by warp 0: lane (i = lane & 7) = row, pivot column broadcast by shuffles; the unit-lower
+    // factor and the pivots go to shared memory (an earlier version let every thread factor the tile redundantly in
+    // registers: no barrier, but 4-8 x the FP64 work, which saturated the FP64 pipe of the small fronts)
+    if (warp == 0) {
+      const int i = lane & 7;
+      double a[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = (j <= i) ? P[(size_t)(c0 + i) * ldx + c0 + j] : 0.0;
+      for (int j = 0; j < 8; ++j) a[j] = (j <= i) ? P[(size_t)(c0 + i) * ldx + c0 + j] : 0.0;
+      bool ok = true;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) {
-      const double d = __shfl_sync(0xffffffffu, a[p], p);
-      dl[p] = d;
-      const double l = a[p] / d;
+      for (int p = 0; p < 8; ++p) {
+        const double d = __shfl_sync(0xffffffffu, a[p], p);
+        ok = ok && (fabs(d) > 1e-300) && isfinite(d);
+        const double inv = rcp_newton(d);
+        const double l = a[p] * inv;
 #pragma unroll
-      for (int j = p + 1; j < 8; ++j) {
-        const double ajp = __shfl_sync(0xffffffffu, a[p], j);
-        if (j <= i) a[j] = fma(-l, ajp, a[j]);
+        for (int j = p + 1; j < 8; ++j) {
+          const double ajp = __shfl_sync(0xffffffffu, a[p], j);
+          if (j <= i) a[j] = fma(-l, ajp, a[j]);
+        }
+        if (i > p) a[p] = l;
+        if (lane == p) { dval[c0 + p] = d; dinv[c0 + p] = inv; }
       }
-      if (i > p) a[p] = l;
+      if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Ld[(size_t)(c0 + i) * 8 + j] = (j < i) ? a[j] : 0.0;
+      }
+      if (!ok && lane == 0) atomicExch(bad, 1);
     }
-    double Lq[8][8];                             // Lq[j][t], t < j: unit-lower factor, replicated in every lane
-#pragma unroll
-    for (int j = 1; j < 8; ++j)
-#pragma unroll
-      for (int t = 0; t < j; ++t) Lq[j][t] = __shfl_sync(0xffffffffu, a[t], j);
-    if (warp == 0 && lane < 8) {
-      double d = dl[0];
-#pragma unroll
-      for (int p = 1; p < 8; ++p) if (i == p) d = dl[p];
-      if (!(fabs(d) > 1e-300) || !isfinite(d)) atomicExch(bad, 1);
-      dval[c0 + i] = d;
-      dinv[c0 + i] = 1.0 / d;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) Ld[(size_t)(c0 + i) * 8 + j] = (j < i) ? a[j] : 0.0;
-    }
-    // rows below the pivot tile: X = A L^-T, one thread per row
+    __syncthreads();
+    // rows below the pivot tile: X = A L^-T, one thread per row, L broadcast from shared memory
     for (int r = c0 + 8 + tid; r < m; r += NT) {
       double *row = P + (size_t)r * ldx + c0;
+      const double *Lt = Ld + (size_t)c0 * 8;
       double x[8];
 #pragma unroll
       for (int j = 0; j < 8; j += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + j); x[j] = v.x; x[j + 1] = v.y; }
 #pragma unroll
-      for (int j = 1; j < 8; ++j)
+      for (int j = 1; j < 8; ++j) {
 #pragma unroll
-        for (int t = 0; t < j; ++t) x[j] = fma(-x[t], Lq[j][t], x[j]);
+        for (int t = 0; t < j; t += 2) {
+          const double2 lv = *reinterpret_cast<const double2 *>(Lt + j * 8 + t);
+          x[j] = fma(-x[t], lv.x, x[j]);
+          if (t + 1 < j) x[j] = fma(-x[t + 1], lv.y, x[j]);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(row + j) = make_double2(x[j], x[j + 1]);
     }
@@ -171,42 +198,65 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   // ---- factor panel -> global: unit-lower L (pivot tiles hold D on the diagonal), L = X D^-1 below --------------
   {
     double *Lo = Lst + (size_t)cell * l_stride + F.l_off;
-    for (int idx = tid; idx < m * s8; idx += NT) {
-      const int r = idx / s8, c = idx - r * s8;
-      double v = 0.0;
-      if (r < s8 && (r >> 3) == (c >> 3)) v = r == c ? dval[c] : (r > c ? Ld[(size_t)r * 8 + (c & 7)] : 0.0);
-      else if (r > c) v = P[(size_t)r * ldx + c] * dinv[c];
-      Lo[idx] = v;
-    }
+    for (int r = warp; r < s8; r += NW)
+      for (int c = lane; c < s8; c += 32) {
+        double v = 0.0;
+        if ((r >> 3) == (c >> 3)) v = r == c ? dval[c] : (r > c ? Ld[(size_t)r * 8 + (c & 7)] : 0.0);
+        else if (r > c) v = P[(size_t)r * ldx + c] * dinv[c];
+        Lo[(size_t)r * s8 + c] = v;
+      }
+    // rows below the own block: a warp covers 32 / s8 rows at once when the panel is narrow
+    const int rpw = s8 >= 32 ? 1 : 32 / s8;
+    const int lr = s8 >= 32 ? 0 : lane / s8, lc = s8 >= 32 ? lane : lane - lr * s8;
+    if (lr < rpw)
+      for (int r = s8 + warp * rpw + lr; r < m; r += NW * rpw)
+        for (int c = lc; c < s8; c += 32) Lo[(size_t)r * s8 + c] = P[(size_t)r * ldx + c] * dinv[c];
   }
 
-  // ---- contribution block: C(I, J) = sum_children C_child - X_I L_J^T, one 8 x 8 tile per warp step --------------
+  // ---- contribution block: C(I, J) = sum_children C_child - X_I L_J^T.  A warp step = one tile column J x four row tiles:
+  // the children are gathered through `pinv` straight into the accumulators, the four MMA chains run interleaved ------
   if (u8 > 0) {
     const int UT = u8 / 8, RT = (u8 + kr) / 8, ldc = u8 + kr;
     double *Co = Cst + (size_t)cell * c_stride + F.c_off;
     const double *Cbase = Cst + (size_t)cell * c_stride;
-    int cnt = 0;
-    for (int J = 0; J < UT; ++J) {
+    int J = 0, gi = warp;
+    while (J < UT) {
+      const int ng = (RT - J + 3) >> 2;
+      if (gi >= ng) { gi -= ng; ++J; continue; }
+      const int I0 = J + 4 * gi;
       const int colp = s8 + J * 8 + fr;
-      const double *Arow = P + (size_t)colp * ldx + fk;
-      for (int I = J; I < RT; ++I, ++cnt) {
-        if (cnt % NW != warp) continue;
-        const int rowp = s8 + I * 8 + 2 * fk;
-        double a0 = 0.0, a1 = 0.0;
-        for (int ci = 0; ci < nch; ++ci) {
-          const int *pv = pinv_s + ci * m;
-          const int jc = pv[colp];
-          if (jc < 0) continue;
-          const double *cb = Cbase + ch_coff[ci] + (size_t)jc * ch_ldc[ci];
-          const int i0 = pv[rowp], i1 = pv[rowp + 1];
-          if (i0 >= 0 && rowp >= colp) a0 += cb[i0];
-          if (i1 >= 0 && rowp + 1 >= colp) a1 += cb[i1];
+      double acc[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+      for (int ci = 0; ci < nch; ++ci) {
+        const int *pv = pinv_s + ci * m;
+        const int jc = pv[colp];
+        if (jc < 0) continue;
+        const double *cb = Cbase + ch_coff[ci] + (size_t)jc * ch_ldc[ci];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int I = I0 + u;
+          if (I >= RT) continue;
+          const int rowp = s8 + I * 8 + 2 * fk;
+          const int2 ii = *reinterpret_cast<const int2 *>(pv + rowp);
+          if (ii.x >= 0 && rowp >= colp) acc[u][0] += cb[ii.x];
+          if (ii.y >= 0 && rowp + 1 >= colp) acc[u][1] += cb[ii.y];
         }
-        const double *Brow = P + (size_t)(s8 + I * 8 + fr) * ldx + fk;
-#pragma unroll 2
-        for (int t = 0; t < s8; t += 4) dmma_m8n8k4(a0, a1, -Arow[t] * dinv[t + fk], Brow[t]);
-        *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + I * 8 + 2 * fk) = make_double2(a0, a1);
       }
+      const double *Arow = P + (size_t)colp * ldx + fk;
+      const double *Brow[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) Brow[u] = P + (size_t)(s8 + min(I0 + u, RT - 1) * 8 + fr) * ldx + fk;
+      for (int t = 0; t < s8; t += 4) {
+        const double a = -Arow[t] * dinv[t + fk];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (I0 + u < RT)
+          *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + (I0 + u) * 8 + 2 * fk) = make_double2(acc[u][0], acc[u][1]);
+      gi += NW;
     }
   }
 }
@@ -216,36 +266,63 @@ template <int NT>
 __global__ void __launch_bounds__(NT)
 k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t l_stride, double *__restrict__ xT) {
   extern __shared__ __align__(16) double mf_smem[];
+  constexpr int NW = NT / 32;
   const int f = M.level_fronts[lf_off + blockIdx.x];
   const MfFront F = M.fronts[f];
-  const int cell = blockIdx.y, tid = threadIdx.x;
+  const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s8 = F.s8, u8 = F.u8, kr = M.kr, NP = M.NP;
   double *L11 = mf_smem;                       // [s8][s8]
   double *ts = L11 + (size_t)s8 * s8;          // [s8][kr]  z, then t, then x
   double *xu = ts + (size_t)s8 * kr;           // [u8][kr]  x of the reached unknowns
   const double *Lp = Lst + (size_t)cell * l_stride + F.l_off;   // [m][s8]
   double *xc = xT + (size_t)cell * k * NP;
-  for (int idx = tid; idx < u8 * kr; idx += NT) {
-    const int j = idx / u8, r = idx - j * u8;
-    const int p = M.front_idx[F.idx_off + s8 + r];
-    xu[r * kr + j] = (p >= 0 && j < k) ? xc[(size_t)j * NP + p] : 0.0;
+  for (int j = warp; j < kr; j += NW) {
+    if (j < k) {
+      for (int r = lane; r < u8; r += 32) {
+        const int p = M.front_idx[F.idx_off + s8 + r];
+        xu[r * kr + j] = p >= 0 ? xc[(size_t)j * NP + p] : 0.0;
+      }
+    } else {
+      for (int r = lane; r < u8; r += 32) xu[r * kr + j] = 0.0;
+    }
+    for (int c = lane; c < s8; c += 32) ts[c * kr + j] = Lp[(size_t)(s8 + u8 + j) * s8 + c];
   }
   for (int idx = tid; idx < s8 * s8; idx += NT) L11[idx] = Lp[idx];
-  for (int idx = tid; idx < kr * s8; idx += NT) {
-    const int j = idx / s8, c = idx - j * s8;
-    ts[c * kr + j] = Lp[(size_t)(s8 + u8 + j) * s8 + c];
-  }
   __syncthreads();
-  // t = z - L21^T x_reached
+  // t = z - L21^T x_reached.  L21 streams through shared memory in chunks of CH rows (one coalesced copy with many
+  // loads in flight; reading it straight from global memory left every thread waiting on its own dependent loads);
+  // a thread owns one column c and 4 right-hand sides.
   if (u8 > 0) {
     const double *L21 = Lp + (size_t)s8 * s8;
-    for (int o = tid; o < s8 * kr; o += NT) {
-      const int j = o / s8, c = o - j * s8;
-      double acc = 0.0;
-      for (int r = 0; r < u8; ++r) acc = fma(L21[(size_t)r * s8 + c], xu[r * kr + j], acc);
-      ts[c * kr + j] -= acc;
+    double *stage = xu + (size_t)u8 * kr;
+    const int CH = mf_bwd_chunk(s8, u8);
+    const int items = s8 * (kr / 4);
+    for (int r0 = 0; r0 < u8; r0 += CH) {
+      const int nr = min(CH, u8 - r0);
+      {
+        const double2 *src = reinterpret_cast<const double2 *>(L21 + (size_t)r0 * s8);
+        double2 *dst = reinterpret_cast<double2 *>(stage);
+        const int n2 = (nr * s8) >> 1;
+        for (int i = tid; i < n2; i += NT) dst[i] = src[i];
+      }
+      __syncthreads();
+      for (int o = tid; o < items; o += NT) {
+        const int jg = o / s8, c = o - jg * s8;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        const double *xr = xu + (size_t)r0 * kr + jg * 4;
+#pragma unroll 4
+        for (int r = 0; r < nr; ++r) {
+          const double l = stage[r * s8 + c];
+          const double2 x0 = *reinterpret_cast<const double2 *>(xr + r * kr);
+          const double2 x1 = *reinterpret_cast<const double2 *>(xr + r * kr + 2);
+          acc[0] = fma(l, x0.x, acc[0]); acc[1] = fma(l, x0.y, acc[1]);
+          acc[2] = fma(l, x1.x, acc[2]); acc[3] = fma(l, x1.y, acc[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ts[c * kr + jg * 4 + i] -= acc[i];
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   // L11^T x = t, 8 unknowns at a time, last tile first
   for (int p = s8 / 8 - 1; p >= 0; --p) {
@@ -262,19 +339,19 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
       for (int i = 0; i < 8; ++i) ts[(c0 + i) * kr + tid] = x[i];
     }
     __syncthreads();
-    for (int o = tid; o < c0 * kr; o += NT) {
-      const int j = o / c0, cp = o - j * c0;
-      double acc = 0.0;
+    if (c0 > 0) {
+      for (int j = warp; j < kr; j += NW)
+        for (int cp = lane; cp < c0; cp += 32) {
+          double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc = fma(L11[(size_t)(c0 + i) * s8 + cp], ts[(c0 + i) * kr + j], acc);
-      ts[cp * kr + j] -= acc;
+          for (int i = 0; i < 8; ++i) acc = fma(L11[(size_t)(c0 + i) * s8 + cp], ts[(c0 + i) * kr + j], acc);
+          ts[cp * kr + j] -= acc;
+        }
+      __syncthreads();
     }
-    __syncthreads();
   }
-  for (int o = tid; o < s8 * k; o += NT) {
-    const int j = o / s8, c = o - j * s8;
-    xc[(size_t)j * NP + F.own_base + c] = ts[c * kr + j];
-  }
+  for (int j = warp; j < k; j += NW)
+    for (int c = lane; c < s8; c += 32) xc[(size_t)j * NP + F.own_base + c] = ts[c * kr + j];
 }
 
 }  // namespace

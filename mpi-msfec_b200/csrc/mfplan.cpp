@@ -25,8 +25,10 @@ size_t mf_smem_forward(const MfFront &f, int n_children, int kr) {
 }
 
 size_t mf_smem_backward(const MfFront &f, int kr) {
-  // L11 (s8 x s8) + t (s8 x kr) + x of the reached unknowns (u8 x kr); equals mf_bwd_smem_bytes (mf.cuh)
-  return ((size_t)f.s8 * f.s8 + (size_t)kr * f.s8 + (size_t)f.u8 * kr) * sizeof(double);
+  // L11 (s8 x s8) + t (s8 x kr) + x of the reached unknowns (u8 x kr) + staged rows of L21; equals mf_bwd_smem_bytes (mf.cuh)
+  const int cap = (6144 / f.s8) & ~7;
+  const int chunk = f.u8 < cap ? f.u8 : (cap < 8 ? 8 : cap);
+  return ((size_t)f.s8 * f.s8 + (size_t)kr * f.s8 + (size_t)f.u8 * kr + (size_t)chunk * f.s8) * sizeof(double);
 }
 
 namespace {
@@ -43,6 +45,8 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget, int min_cells) {
   P.kr = (t.k_solve + 7) / 8 * 8;
   const int kr = P.kr;
   if (const char *e = std::getenv("MSFEC_MF_MIN_CELLS")) min_cells = std::max(1, std::atoi(e));
+  // MSFEC_MF_SMEM_KB: tighter shared-memory budget per front (more CTAs per SM at the top of the tree, longer chains)
+  if (const char *e = std::getenv("MSFEC_MF_SMEM_KB")) smem_budget = std::min(smem_budget, std::max(16, std::atoi(e)) * 1024);
 
   // ---- nested dissection in doubled integer coordinates 0 .. 2n ----------------------------------------
   struct Dof { int row; int p[3]; };
