@@ -975,6 +975,7 @@ class Engine {
   } mf_;
   double *d_mf_L_ = nullptr, *d_mf_C_ = nullptr, *d_mf_xT_ = nullptr;
   long mf_alloc_ = 0;                        // cells the multifrontal buffers are allocated for
+  std::vector<int> mf_level_S_;              // per level: common panel width / 8 of its fronts (0: generic kernel)
   cudaEvent_t ev_mf_[2]{};
   std::vector<cudaEvent_t> mf_marks_;        // 3 events per sub-batch: before forward, between, after backward
   size_t mf_marks_used_ = 0;
@@ -1231,10 +1232,23 @@ void Engine::upload_mf() {
   int max_f = 0, max_b = 0;
   for (int v : MF_.smem_fwd) max_f = std::max(max_f, v);
   for (int v : MF_.smem_bwd) max_b = std::max(max_b, v);
-  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<128, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
-  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<256, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
-  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
+  // per level: common panel width of its fronts in 8-column tiles (0: mixed widths or wider than the templated kernels)
+  mf_level_S_.assign(MF_.n_levels, 0);
+  for (int l = 0; l < MF_.n_levels; ++l) {
+    int w = -1;
+    for (int i = MF_.level_off[l]; i < MF_.level_off[l + 1]; ++i) {
+      const int s8 = MF_.fronts[MF_.level_fronts[i]].s8;
+      w = (w == -1 || w == s8) ? s8 : 0;
+    }
+    if (std::getenv("MSFEC_MF_GENERIC") == nullptr && w > 0 && w / 8 <= 6) mf_level_S_[l] = w / 8;
+  }
+#define MF_SET_ATTR(NT, MINB, S) CUDA_OK(cudaFuncSetAttribute(k_mf_forward<NT, MINB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
+#define MF_SET_ATTR_ALL(S) MF_SET_ATTR(128, 6, S) MF_SET_ATTR(256, 2, S) MF_SET_ATTR(512, 1, S)
+  MF_SET_ATTR_ALL(0) MF_SET_ATTR_ALL(1) MF_SET_ATTR_ALL(2) MF_SET_ATTR_ALL(3) MF_SET_ATTR_ALL(4) MF_SET_ATTR_ALL(5) MF_SET_ATTR_ALL(6)
+#undef MF_SET_ATTR_ALL
+#undef MF_SET_ATTR
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
+  CUDA_OK(cudaFuncSetAttribute(k_mf_backward<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
   for (auto &ev : ev_mf_) CUDA_OK(cudaEventCreate(&ev));
 }
 
@@ -1275,21 +1289,35 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
       const int nfl = MF_.level_off[l + 1] - MF_.level_off[l];
       const size_t sm = (size_t)MF_.smem_fwd[l];
       // threads per front by its shared-memory footprint: small fronts share an SM (6 CTAs of 4 warps), fronts that own an SM
-      // get 16 warps to hide the latency of the children gathers
-      if (sm <= 56 * 1024)
-        k_mf_forward<128, 6><<<dim3(nfl, nc), 128, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
-                                                                 d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
-      else if (sm <= 112 * 1024)
-        k_mf_forward<256, 2><<<dim3(nfl, nc), 256, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
-                                                                 d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
-      else
-        k_mf_forward<512, 1><<<dim3(nfl, nc), 512, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, k, lo,
-                                                                 d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2);
+      // get 16 warps to hide the latency of the children gathers; panel width as a template argument where the level is uniform
+#define MF_LAUNCH(NT, MINB, S)                                                                                                 \
+  k_mf_forward<NT, MINB, S><<<dim3(nfl, nc), NT, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, \
+                                                                k, lo, d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2)
+#define MF_LAUNCH_S(S)                                                     \
+  do {                                                                     \
+    if (sm <= 56 * 1024) MF_LAUNCH(128, 6, S);                             \
+    else if (sm <= 112 * 1024) MF_LAUNCH(256, 2, S);                       \
+    else MF_LAUNCH(512, 1, S);                                             \
+  } while (0)
+      switch (mf_level_S_[l]) {
+        case 1: MF_LAUNCH_S(1); break;
+        case 2: MF_LAUNCH_S(2); break;
+        case 3: MF_LAUNCH_S(3); break;
+        case 4: MF_LAUNCH_S(4); break;
+        case 5: MF_LAUNCH_S(5); break;
+        case 6: MF_LAUNCH_S(6); break;
+        default: MF_LAUNCH_S(0); break;
+      }
+#undef MF_LAUNCH_S
+#undef MF_LAUNCH
     }
     CUDA_OK(cudaEventRecord(mf_marks_[mf_marks_used_ + 1], stream_));
     for (int l = MF_.n_levels - 1; l >= 0; --l) {
       const int nfl = MF_.level_off[l + 1] - MF_.level_off[l];
-      k_mf_backward<128><<<dim3(nfl, nc), 128, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
+      if (MF_.smem_bwd[l] <= 112 * 1024)
+        k_mf_backward<128><<<dim3(nfl, nc), 128, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
+      else
+        k_mf_backward<256><<<dim3(nfl, nc), 256, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
     }
     CUDA_OK(cudaEventRecord(mf_marks_[mf_marks_used_ + 2], stream_));
     mf_marks_used_ += 3;

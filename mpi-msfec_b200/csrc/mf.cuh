@@ -7,14 +7,14 @@
 //                  cell-independent coupling entries, padding pivots) + rhs rows + the leading columns of the
 //                  children's contribution blocks (extend-add through `cmap`);
 //                  LDL^T of the own block / X = A L^-T of the rows below in 8-column steps: the left-looking update
-//                  runs on mma.sync.m8n8k4.f64, the 8 x 8 pivot tile is factored redundantly by every warp in
-//                  registers (no broadcast, one barrier less), the rows below are solved one thread per row;
-//                  factor panel -> global (read again by k_mf_backward only);
+//                  runs on mma.sync.m8n8k4.f64, the 8 x 8 pivot tile is factored by one warp (lane = row, shuffles),
+//                  the rows below are solved one thread per row;
+//                  factor record -> global (read again by k_mf_backward only);
 //                  contribution block C = sum_children C_child - X L21^T, 8 x 8 tiles on the FP64 tensor cores,
 //                  children gathered through `pinv` straight into the accumulators, 16-byte stores.
-//   k_mf_backward  x_own = L11^-T (z_own - L21^T x_reached), top-down.
-// Everything else of a front lives in shared memory, so HBM sees: slot values and rhs once, every factor panel
-// written once and read once, every contribution block written once and read once (MfPlan::bytes).
+//   k_mf_backward  x_own = L11^-T (z_own - L21^T x_reached), top-down; the product on the FP64 tensor cores.
+// Everything else of a front lives in shared memory, so HBM sees: slot values and rhs once, every factor record
+// written once and read once, every contribution block written once and read once (MfPlan::bytes_fwd / _bwd).
 // Included by engine.cu.
 #pragma once
 
@@ -31,21 +31,25 @@ struct MfDev {
 
 constexpr int kMfMaxChildren = 8;
 
-// dynamic shared memory of k_mf_forward (doubles first, then the children's inverse maps)
+// Per-front record in the factor storage (written by k_mf_forward, read by k_mf_backward): the shared-memory image of
+// the forward kernel, copied verbatim (one flat coalesced copy each way, no index arithmetic):
+//   [ panel m x ldx | 1/d (s8) | d (s8) | unit-lower factors of the 8 x 8 pivot tiles (s8 x 8) ]
+// Panel rows below a pivot tile hold X = L D (unscaled); the consumers multiply by 1/d.
+__host__ __device__ inline int mf_record_doubles(int m, int ldx, int s8) { return m * ldx + 10 * s8; }
+
+// dynamic shared memory of k_mf_forward: the record, then the children's inverse maps
 __host__ __device__ inline size_t mf_fwd_smem_bytes(int m, int ldx, int s8, int nch) {
-  return ((size_t)m * ldx + 2 * (size_t)s8 + 8 * (size_t)s8) * sizeof(double) + (size_t)nch * m * sizeof(int);
+  return (size_t)mf_record_doubles(m, ldx, s8) * sizeof(double) + (size_t)nch * m * sizeof(int);
 }
-// rows of L21 staged at once by k_mf_backward: the whole block when it is small, else ~48 KB worth (multiple of 8)
-__host__ __device__ inline int mf_bwd_chunk(int s8, int u8) {
-  const int cap = (6144 / s8) & ~7;
-  return u8 < cap ? u8 : (cap < 8 ? 8 : cap);
-}
-__host__ __device__ inline size_t mf_bwd_smem_bytes(int s8, int u8, int kr) {
-  return ((size_t)s8 * s8 + (size_t)s8 * kr + (size_t)u8 * kr + (size_t)mf_bwd_chunk(s8, u8) * s8) * sizeof(double);
+// k_mf_backward: the record, x of the reached unknowns (u8 x (kr + 4)) and t / x of the own unknowns (s8 x (kr + 4))
+__host__ __device__ inline size_t mf_bwd_smem_bytes(int m, int ldx, int s8, int u8, int kr) {
+  return ((size_t)mf_record_doubles(m, ldx, s8) + (size_t)(u8 + s8) * (kr + 4)) * sizeof(double);
 }
 
-// grid (fronts of the level, cells of the sub-batch), block NT
-template <int NT, int MINB>
+// grid (fronts of the level, cells of the sub-batch), block NT.  S > 0: every front of the level has s8 = 8 S own
+// columns (compile-time panel width: the k-loops unroll and the A fragments of a tile column stay in registers);
+// S = 0: run-time width.
+template <int NT, int MINB, int S>
 __global__ void __launch_bounds__(NT, MINB)
 k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, double kscale,
              const double *__restrict__ b, int NI, int k, int cell_lo, double *__restrict__ Lst, size_t l_stride,
@@ -53,24 +57,26 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   extern __shared__ __align__(16) double mf_smem[];
   __shared__ int ch_coff[kMfMaxChildren], ch_ldc[kMfMaxChildren];
   constexpr int NW = NT / 32;
+  constexpr int KA = S > 0 ? 2 * S : 1;          // k-steps of a full-width product
   const int f = M.level_fronts[lf_off + blockIdx.x];
   const MfFront F = M.fronts[f];
   const int cell = blockIdx.y, gcell = cell_lo + cell, g = gcell / kLanes, ln = gcell % kLanes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;
-  const int s8 = F.s8, u8 = F.u8, m = F.m, ldx = F.ldx, kr = M.kr;
+  const int s8 = S > 0 ? 8 * S : F.s8, ldx = s8 + 4;
+  const int u8 = F.u8, kr = M.kr, m = s8 + u8 + kr;
   const int nch = F.ch_hi - F.ch_lo;
   double *P = mf_smem;                          // [m][ldx]   the panel
-  double *dinv = P + (size_t)m * ldx;           // [s8]       1 / d
+  double *dinv = P + m * ldx;                   // [s8]       1 / d
   double *dval = dinv + s8;                     // [s8]       d
   double *Ld = dval + s8;                       // [s8][8]    unit-lower factors of the 8 x 8 pivot tiles
-  int *pinv_s = reinterpret_cast<int *>(Ld + 8 * (size_t)s8);   // [nch][m]
+  int *pinv_s = reinterpret_cast<int *>(Ld + 8 * s8);   // [nch][m]
+  const int rec2 = mf_record_doubles(m, ldx, s8) >> 1;
 
   // ---- assemble the panel --------------------------------------------------------------------------------
   {
     double2 *P2 = reinterpret_cast<double2 *>(P);
-    const int n2 = (m * ldx) >> 1;
-    for (int i = tid; i < n2; i += NT) P2[i] = make_double2(0.0, 0.0);
+    for (int i = tid; i < rec2; i += NT) P2[i] = make_double2(0.0, 0.0);
   }
   __syncthreads();
   {
@@ -85,7 +91,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     for (int c = warp; c < s8; c += NW) {
       const int row = M.own_rows[F.row_off + c];
       if (row < 0) continue;
-      for (int j = lane; j < k; j += 32) P[(size_t)(s8 + u8 + j) * ldx + c] = bc[((size_t)row * k + j) * kLanes];
+      for (int j = lane; j < k; j += 32) P[(s8 + u8 + j) * ldx + c] = bc[((size_t)row * k + j) * kLanes];
     }
   }
   __syncthreads();
@@ -103,24 +109,37 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     for (int j = warp; j < ch.n_own; j += NW) {
       const int cj = cmap[j];
       const double *col = Cc + (size_t)j * ldc;
-#pragma unroll 4
-      for (int i = j + lane; i < ldc; i += 32) {
-        const int ri = cmap[i];
-        const double v = col[i];
-        if (ri >= 0) P[(size_t)ri * ldx + cj] += v;
+      // eight independent loads in flight per lane
+      for (int i0 = j + lane; i0 < ldc; i0 += 256) {
+        double v[8];
+        int ri[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + 32 * u;
+          ri[u] = i < ldc ? cmap[i] : -1;
+          v[u] = i < ldc ? col[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (ri[u] >= 0) P[ri[u] * ldx + cj] += v[u];
       }
     }
     __syncthreads();
   }
 
   // ---- factor: 8 columns at a time ---------------------------------------------------------------------------
-  const int S = s8 / 8, MT = m / 8;
-  for (int q = 0; q < S; ++q) {
+  const int NS = s8 / 8, MT = m / 8;
+#pragma unroll
+  for (int q = 0; q < (S > 0 ? S : NS); ++q) {
     const int c0 = q * 8;
     if (q > 0) {
       // left-looking update of tile column q:  P(R, q) -= X(R, 0:c0) L(q, 0:c0)^T   (L = X D^-1), four row tiles of a
       // warp at a time (independent accumulator chains).  MMA m = column inside the tile, n = row, k = earlier columns
-      const double *Arow = P + (size_t)(c0 + fr) * ldx + fk;
+      const double *Arow = P + (c0 + fr) * ldx + fk;
+      double af[KA];
+      if (S > 0) {
+#pragma unroll
+        for (int t = 0; t < KA; ++t) af[t] = t < 2 * q ? -Arow[4 * t] * dinv[4 * t + fk] : 0.0;
+      }
       for (int R0 = q + warp; R0 < MT; R0 += 4 * NW) {
         double acc[4][2];
         double *tp[4];
@@ -128,14 +147,23 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int R = min(R0 + u * NW, MT - 1);
-          tp[u] = P + (size_t)(R * 8 + 2 * fk) * ldx + c0 + fr;
-          Brow[u] = P + (size_t)(R * 8 + fr) * ldx + fk;
+          tp[u] = P + (R * 8 + 2 * fk) * ldx + c0 + fr;
+          Brow[u] = P + (R * 8 + fr) * ldx + fk;
           acc[u][0] = tp[u][0]; acc[u][1] = tp[u][ldx];
         }
-        for (int t = 0; t < c0; t += 4) {
-          const double a = -Arow[t] * dinv[t + fk];
+        if (S > 0) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+          for (int t = 0; t < KA; ++t)
+            if (t < 2 * q) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], af[t], Brow[u][4 * t]);
+            }
+        } else {
+          for (int t = 0; t < c0; t += 4) {
+            const double a = -Arow[t] * dinv[t + fk];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u)
@@ -150,7 +178,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
       const int i = lane & 7;
       double a[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = (j <= i) ? P[(size_t)(c0 + i) * ldx + c0 + j] : 0.0;
+      for (int j = 0; j < 8; ++j) a[j] = (j <= i) ? P[(c0 + i) * ldx + c0 + j] : 0.0;
       bool ok = true;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
@@ -168,15 +196,15 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
       }
       if (lane < 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Ld[(size_t)(c0 + i) * 8 + j] = (j < i) ? a[j] : 0.0;
+        for (int j = 0; j < 8; ++j) Ld[(c0 + i) * 8 + j] = (j < i) ? a[j] : 0.0;
       }
       if (!ok && lane == 0) atomicExch(bad, 1);
     }
     __syncthreads();
     // rows below the pivot tile: X = A L^-T, one thread per row, L broadcast from shared memory
     for (int r = c0 + 8 + tid; r < m; r += NT) {
-      double *row = P + (size_t)r * ldx + c0;
-      const double *Lt = Ld + (size_t)c0 * 8;
+      double *row = P + r * ldx + c0;
+      const double *Lt = Ld + c0 * 8;
       double x[8];
 #pragma unroll
       for (int j = 0; j < 8; j += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + j); x[j] = v.x; x[j + 1] = v.y; }
@@ -195,73 +223,98 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     __syncthreads();
   }
 
-  // ---- factor panel -> global: unit-lower L (pivot tiles hold D on the diagonal), L = X D^-1 below --------------
+  // ---- factor record -> global: the shared-memory image as it is ---------------------------------------------------
   {
-    double *Lo = Lst + (size_t)cell * l_stride + F.l_off;
-    for (int r = warp; r < s8; r += NW)
-      for (int c = lane; c < s8; c += 32) {
-        double v = 0.0;
-        if ((r >> 3) == (c >> 3)) v = r == c ? dval[c] : (r > c ? Ld[(size_t)r * 8 + (c & 7)] : 0.0);
-        else if (r > c) v = P[(size_t)r * ldx + c] * dinv[c];
-        Lo[(size_t)r * s8 + c] = v;
-      }
-    // rows below the own block: a warp covers 32 / s8 rows at once when the panel is narrow
-    const int rpw = s8 >= 32 ? 1 : 32 / s8;
-    const int lr = s8 >= 32 ? 0 : lane / s8, lc = s8 >= 32 ? lane : lane - lr * s8;
-    if (lr < rpw)
-      for (int r = s8 + warp * rpw + lr; r < m; r += NW * rpw)
-        for (int c = lc; c < s8; c += 32) Lo[(size_t)r * s8 + c] = P[(size_t)r * ldx + c] * dinv[c];
+    double2 *Lo = reinterpret_cast<double2 *>(Lst + (size_t)cell * l_stride + F.l_off);
+    const double2 *P2 = reinterpret_cast<const double2 *>(P);
+    for (int i = tid; i < rec2; i += NT) Lo[i] = P2[i];
   }
 
-  // ---- contribution block: C(I, J) = sum_children C_child - X_I L_J^T.  A warp step = one tile column J x four row tiles:
-  // the children are gathered through `pinv` straight into the accumulators, the four MMA chains run interleaved ------
+  // ---- contribution block: C(I, J) = sum_children C_child - X_I L_J^T.  A warp owns tile columns J (dealt in snake
+  // order, long and short columns alternate); per column the A fragments are scaled once and kept in registers (S > 0);
+  // four row tiles per step: the children are gathered through `pinv` straight into the accumulators and the four MMA
+  // chains run interleaved ---------------------------------------------------------------------------------------------
   if (u8 > 0) {
     const int UT = u8 / 8, RT = (u8 + kr) / 8, ldc = u8 + kr;
     double *Co = Cst + (size_t)cell * c_stride + F.c_off;
     const double *Cbase = Cst + (size_t)cell * c_stride;
-    int J = 0, gi = warp;
-    while (J < UT) {
-      const int ng = (RT - J + 3) >> 2;
-      if (gi >= ng) { gi -= ng; ++J; continue; }
-      const int I0 = J + 4 * gi;
+    for (int rnd = 0; rnd * NW < UT; ++rnd) {
+      const int J = rnd * NW + ((rnd & 1) ? NW - 1 - warp : warp);
+      if (J >= UT) continue;
       const int colp = s8 + J * 8 + fr;
-      double acc[4][2];
+      const double *Arow = P + colp * ldx + fk;
+      double af[KA];
+      if (S > 0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
-      for (int ci = 0; ci < nch; ++ci) {
-        const int *pv = pinv_s + ci * m;
-        const int jc = pv[colp];
-        if (jc < 0) continue;
-        const double *cb = Cbase + ch_coff[ci] + (size_t)jc * ch_ldc[ci];
+        for (int t = 0; t < KA; ++t) af[t] = -Arow[4 * t] * dinv[4 * t + fk];
+      }
+      // fronts of a dissection tree have at most two children (fast path); more take the loop below
+      int jc[2];
+      const double *cb[2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int I = I0 + u;
-          if (I >= RT) continue;
-          const int rowp = s8 + I * 8 + 2 * fk;
-          const int2 ii = *reinterpret_cast<const int2 *>(pv + rowp);
-          if (ii.x >= 0 && rowp >= colp) acc[u][0] += cb[ii.x];
-          if (ii.y >= 0 && rowp + 1 >= colp) acc[u][1] += cb[ii.y];
+      for (int ci = 0; ci < 2; ++ci) {
+        jc[ci] = ci < nch ? pinv_s[ci * m + colp] : -1;
+        cb[ci] = jc[ci] >= 0 ? Cbase + ch_coff[ci] + (size_t)jc[ci] * ch_ldc[ci] : Cbase;
+      }
+      for (int I0 = J; I0 < RT; I0 += 4) {
+        double acc[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          if (jc[ci] < 0) continue;
+          const int *pv = pinv_s + ci * m;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int I = I0 + u;
+            if (I >= RT) continue;
+            const int rowp = s8 + I * 8 + 2 * fk;
+            const int2 ii = *reinterpret_cast<const int2 *>(pv + rowp);
+            if (ii.x >= 0 && rowp >= colp) acc[u][0] += cb[ci][ii.x];
+            if (ii.y >= 0 && rowp + 1 >= colp) acc[u][1] += cb[ci][ii.y];
+          }
         }
+        for (int ci = 2; ci < nch; ++ci) {
+          const int *pv = pinv_s + ci * m;
+          const int jcc = pv[colp];
+          if (jcc < 0) continue;
+          const double *cbb = Cbase + ch_coff[ci] + (size_t)jcc * ch_ldc[ci];
+          for (int u = 0; u < 4; ++u) {
+            const int I = I0 + u;
+            if (I >= RT) continue;
+            const int rowp = s8 + I * 8 + 2 * fk;
+            if (pv[rowp] >= 0 && rowp >= colp) acc[u][0] += cbb[pv[rowp]];
+            if (pv[rowp + 1] >= 0 && rowp + 1 >= colp) acc[u][1] += cbb[pv[rowp + 1]];
+          }
+        }
+        const double *Brow[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) Brow[u] = P + (s8 + min(I0 + u, RT - 1) * 8 + fr) * ldx + fk;
+        if (S > 0) {
+#pragma unroll
+          for (int t = 0; t < KA; ++t) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], af[t], Brow[u][4 * t]);
+          }
+        } else {
+          for (int t = 0; t < s8; t += 4) {
+            const double a = -Arow[t] * dinv[t + fk];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (I0 + u < RT)
+            *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + (I0 + u) * 8 + 2 * fk) = make_double2(acc[u][0], acc[u][1]);
       }
-      const double *Arow = P + (size_t)colp * ldx + fk;
-      const double *Brow[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) Brow[u] = P + (size_t)(s8 + min(I0 + u, RT - 1) * 8 + fr) * ldx + fk;
-      for (int t = 0; t < s8; t += 4) {
-        const double a = -Arow[t] * dinv[t + fk];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (I0 + u < RT)
-          *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + (I0 + u) * 8 + 2 * fk) = make_double2(acc[u][0], acc[u][1]);
-      gi += NW;
     }
   }
 }
 
 // grid (fronts of the level, cells of the sub-batch), block NT.  xT[cell][k][NP] holds x in the padded elimination order.
+// The front's record comes back into shared memory with one flat copy; t = D^-1 (X_z - X21^T x_reached) runs on the FP64
+// tensor cores (m = own column, n = right-hand side, k = reached unknown), then L11^T x = t tile by tile.
 template <int NT>
 __global__ void __launch_bounds__(NT)
 k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t l_stride, double *__restrict__ xT) {
@@ -270,73 +323,60 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   const int f = M.level_fronts[lf_off + blockIdx.x];
   const MfFront F = M.fronts[f];
   const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int s8 = F.s8, u8 = F.u8, kr = M.kr, NP = M.NP;
-  double *L11 = mf_smem;                       // [s8][s8]
-  double *ts = L11 + (size_t)s8 * s8;          // [s8][kr]  z, then t, then x
-  double *xu = ts + (size_t)s8 * kr;           // [u8][kr]  x of the reached unknowns
-  const double *Lp = Lst + (size_t)cell * l_stride + F.l_off;   // [m][s8]
+  const int fr = lane >> 2, fk = lane & 3;
+  const int s8 = F.s8, u8 = F.u8, kr = M.kr, NP = M.NP, ldx = s8 + 4, m = s8 + u8 + kr, ldt = kr + 4;
+  double *P = mf_smem;                          // [m][ldx]
+  const double *dinv = P + m * ldx;             // [s8]
+  const double *Ld = dinv + 2 * s8;             // [s8][8]
+  const int rec = mf_record_doubles(m, ldx, s8);
+  double *xu = P + rec;                         // [u8][ldt]  x of the reached unknowns
+  double *ts = xu + u8 * ldt;                   // [s8][ldt]  t, then x of the own unknowns
   double *xc = xT + (size_t)cell * k * NP;
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(Lst + (size_t)cell * l_stride + F.l_off);
+    double2 *dst = reinterpret_cast<double2 *>(P);
+    for (int i = tid; i < (rec >> 1); i += NT) dst[i] = src[i];
+  }
   for (int j = warp; j < kr; j += NW) {
     if (j < k) {
       for (int r = lane; r < u8; r += 32) {
         const int p = M.front_idx[F.idx_off + s8 + r];
-        xu[r * kr + j] = p >= 0 ? xc[(size_t)j * NP + p] : 0.0;
+        xu[r * ldt + j] = p >= 0 ? xc[(size_t)j * NP + p] : 0.0;
       }
     } else {
-      for (int r = lane; r < u8; r += 32) xu[r * kr + j] = 0.0;
+      for (int r = lane; r < u8; r += 32) xu[r * ldt + j] = 0.0;
     }
-    for (int c = lane; c < s8; c += 32) ts[c * kr + j] = Lp[(size_t)(s8 + u8 + j) * s8 + c];
   }
-  for (int idx = tid; idx < s8 * s8; idx += NT) L11[idx] = Lp[idx];
   __syncthreads();
-  // t = z - L21^T x_reached.  L21 streams through shared memory in chunks of CH rows (one coalesced copy with many
-  // loads in flight; reading it straight from global memory left every thread waiting on its own dependent loads);
-  // a thread owns one column c and 4 right-hand sides.
-  if (u8 > 0) {
-    const double *L21 = Lp + (size_t)s8 * s8;
-    double *stage = xu + (size_t)u8 * kr;
-    const int CH = mf_bwd_chunk(s8, u8);
-    const int items = s8 * (kr / 4);
-    for (int r0 = 0; r0 < u8; r0 += CH) {
-      const int nr = min(CH, u8 - r0);
-      {
-        const double2 *src = reinterpret_cast<const double2 *>(L21 + (size_t)r0 * s8);
-        double2 *dst = reinterpret_cast<double2 *>(stage);
-        const int n2 = (nr * s8) >> 1;
-        for (int i = tid; i < n2; i += NT) dst[i] = src[i];
-      }
-      __syncthreads();
-      for (int o = tid; o < items; o += NT) {
-        const int jg = o / s8, c = o - jg * s8;
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        const double *xr = xu + (size_t)r0 * kr + jg * 4;
-#pragma unroll 4
-        for (int r = 0; r < nr; ++r) {
-          const double l = stage[r * s8 + c];
-          const double2 x0 = *reinterpret_cast<const double2 *>(xr + r * kr);
-          const double2 x1 = *reinterpret_cast<const double2 *>(xr + r * kr + 2);
-          acc[0] = fma(l, x0.x, acc[0]); acc[1] = fma(l, x0.y, acc[1]);
-          acc[2] = fma(l, x1.x, acc[2]); acc[3] = fma(l, x1.y, acc[3]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ts[c * kr + jg * 4 + i] -= acc[i];
-      }
-      __syncthreads();
+  // t(c, j) = (X_z(j, c) - sum_r X21(r, c) x_reached(r, j)) / d_c : 8 x 8 tiles (c-tile, j-tile) over the warps
+  {
+    const int CT = s8 / 8, JT = kr / 8;
+    for (int tix = warp; tix < CT * JT; tix += NW) {
+      const int ct = tix / JT, jt = tix - ct * JT;
+      double a0 = 0.0, a1 = 0.0;
+      const double *A = P + (s8 + fk) * ldx + ct * 8 + fr;       // A[m = c][k = r] = X21(r, c)
+      const double *B = xu + fk * ldt + jt * 8 + fr;             // B[k = r][n = j] = x_reached(r, j)
+      for (int r0 = 0; r0 < u8; r0 += 4) dmma_m8n8k4(a0, a1, A[r0 * ldx], B[r0 * ldt]);
+      const int c = ct * 8 + fr, j = jt * 8 + 2 * fk;
+      const double di = dinv[c];
+      ts[c * ldt + j] = (P[(s8 + u8 + j) * ldx + c] - a0) * di;
+      ts[c * ldt + j + 1] = (P[(s8 + u8 + j + 1) * ldx + c] - a1) * di;
     }
   }
-  // L11^T x = t, 8 unknowns at a time, last tile first
+  __syncthreads();
+  // L11^T x = t, 8 unknowns at a time, last tile first; below a pivot tile the panel holds X = L D
   for (int p = s8 / 8 - 1; p >= 0; --p) {
     const int c0 = p * 8;
     if (tid < kr) {
       double x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = ts[(c0 + i) * kr + tid];
+      for (int i = 0; i < 8; ++i) x[i] = ts[(c0 + i) * ldt + tid];
 #pragma unroll
       for (int i = 6; i >= 0; --i)
 #pragma unroll
-        for (int i2 = i + 1; i2 < 8; ++i2) x[i] = fma(-L11[(size_t)(c0 + i2) * s8 + c0 + i], x[i2], x[i]);
+        for (int i2 = i + 1; i2 < 8; ++i2) x[i] = fma(-Ld[(c0 + i2) * 8 + i], x[i2], x[i]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ts[(c0 + i) * kr + tid] = x[i];
+      for (int i = 0; i < 8; ++i) ts[(c0 + i) * ldt + tid] = x[i];
     }
     __syncthreads();
     if (c0 > 0) {
@@ -344,14 +384,14 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
         for (int cp = lane; cp < c0; cp += 32) {
           double acc = 0.0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc = fma(L11[(size_t)(c0 + i) * s8 + cp], ts[(c0 + i) * kr + j], acc);
-          ts[cp * kr + j] -= acc;
+          for (int i = 0; i < 8; ++i) acc = fma(P[(c0 + i) * ldx + cp], ts[(c0 + i) * ldt + j], acc);
+          ts[cp * ldt + j] -= acc * dinv[cp];
         }
       __syncthreads();
     }
   }
   for (int j = warp; j < k; j += NW)
-    for (int c = lane; c < s8; c += 32) xc[(size_t)j * NP + F.own_base + c] = ts[c * kr + j];
+    for (int c = lane; c < s8; c += 32) xc[(size_t)j * NP + F.own_base + c] = ts[c * ldt + j];
 }
 
 }  // namespace

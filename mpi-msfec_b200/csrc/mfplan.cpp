@@ -17,18 +17,17 @@ namespace msfec {
 // distinct 8-byte banks
 int mf_ldx(int s8) { return s8 + 4; }
 
+// factor record of a front = shared-memory image of k_mf_forward: panel m x ldx, 1/d, d, pivot-tile factors (mf.cuh)
+static size_t mf_record(const MfFront &f) { return (size_t)f.m * f.ldx + 10 * (size_t)f.s8; }
+
 size_t mf_smem_forward(const MfFront &f, int n_children, int kr) {
-  (void)kr;   // must equal mf_fwd_smem_bytes (mf.cuh): panel, 1/d, d, pivot-tile factors, children's inverse maps
-  size_t b = ((size_t)f.m * f.ldx + 10 * (size_t)f.s8) * sizeof(double);
-  b += (size_t)n_children * f.m * sizeof(int32_t);
-  return (b + 15) / 16 * 16;
+  (void)kr;   // must equal mf_fwd_smem_bytes (mf.cuh): the record + the children's inverse maps
+  return mf_record(f) * sizeof(double) + (size_t)n_children * f.m * sizeof(int32_t);
 }
 
 size_t mf_smem_backward(const MfFront &f, int kr) {
-  // L11 (s8 x s8) + t (s8 x kr) + x of the reached unknowns (u8 x kr) + staged rows of L21; equals mf_bwd_smem_bytes (mf.cuh)
-  const int cap = (6144 / f.s8) & ~7;
-  const int chunk = f.u8 < cap ? f.u8 : (cap < 8 ? 8 : cap);
-  return ((size_t)f.s8 * f.s8 + (size_t)kr * f.s8 + (size_t)f.u8 * kr + (size_t)chunk * f.s8) * sizeof(double);
+  // the record + x of the reached unknowns + t / x of the own unknowns; equals mf_bwd_smem_bytes (mf.cuh)
+  return (mf_record(f) + (size_t)(f.u8 + f.s8) * (kr + 4)) * sizeof(double);
 }
 
 namespace {
@@ -305,7 +304,7 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget, int min_cells) {
   for (auto &F : P.fronts) if (F.parent >= 0 && P.fronts[F.parent].level != F.level + 1) pingpong = false;
   {
     int64_t loff = 0;
-    for (auto &F : P.fronts) { F.l_off = (int32_t)loff; loff += (int64_t)F.m * F.s8; }
+    for (auto &F : P.fronts) { F.l_off = (int32_t)loff; loff += (int64_t)mf_record(F); }
     P.l_doubles = loff;
     if (pingpong) {
       int64_t region[2] = {0, 0};

@@ -44,7 +44,7 @@ struct MfFront {
   int32_t ps_lo, ps_hi;   // cell-independent entries  panel[ps_dest] = ps_val * kscale
   int32_t pc_lo, pc_hi;   // constants (padding pivots 1, pinned pivot -1)
   int32_t ch_lo, ch_hi;   // MfPlan::children[ch_lo .. ch_hi)
-  int32_t l_off;          // per-cell factor storage: m x s8 row-major panel (L, unit diagonal tiles hold D), doubles
+  int32_t l_off;          // per-cell factor storage: the front's record [panel m x ldx | 1/d | d | pivot-tile factors], doubles
   int32_t c_off;          // per-cell contribution storage: column-major (u8 + kr) x u8, doubles
   int32_t n_rows_real;    // s + u (diagnostics)
 };

@@ -219,9 +219,23 @@ def emulate_multifrontal(bb, vals, kscale, b):
             X[j + 1:s8, j] = lcol_own
         Lfull = X.copy()
         Lfull[s8:, :] = X[s8:, :] / d[None, :]
-        out = Lfull.copy()
-        out[np.arange(s8), np.arange(s8)] = d
-        Lst[F["l_off"]:F["l_off"] + m * s8] = out.reshape(-1)
+        # factor record = shared-memory image of k_mf_forward: panel [m][ldx] (rows below a pivot tile hold X = L D, the
+        # pivot tiles themselves are not read again), 1/d, d, unit-lower factors of the 8 x 8 pivot tiles
+        rec = np.zeros(m * ldx + 10 * s8)
+        Pn = rec[:m * ldx].reshape(m, ldx)
+        Pn[s8:, :s8] = X[s8:, :]
+        Ld = np.zeros((s8, 8))
+        for r in range(s8):
+            for c in range(r):
+                if r // 8 == c // 8:
+                    Ld[r, c % 8] = X[r, c]                       # unit-lower L inside the pivot tile
+                else:
+                    Pn[r, c] = X[r, c] * d[c]                    # X = L D below the pivot tile
+            Pn[r, (r // 8) * 8:(r // 8) * 8 + 8] = np.nan        # pivot tile: garbage in the kernel, never read
+        rec[m * ldx:m * ldx + s8] = 1.0 / d
+        rec[m * ldx + s8:m * ldx + 2 * s8] = d
+        rec[m * ldx + 2 * s8:] = Ld.reshape(-1)
+        Lst[F["l_off"]:F["l_off"] + len(rec)] = rec
         dall[F["own_base"]:F["own_base"] + s8] = d
         # contribution block
         if u8:
@@ -252,15 +266,21 @@ def emulate_multifrontal(bb, vals, kscale, b):
     for f in reversed(order_fwd):
         F = fronts[f]
         s8, u8, m = F["s8"], F["u8"], F["m"]
-        Lp = Lst[F["l_off"]:F["l_off"] + m * s8].reshape(m, s8)
+        ldx = F["ldx"]
+        rec = Lst[F["l_off"]:F["l_off"] + m * ldx + 10 * s8]
+        Pn = rec[:m * ldx].reshape(m, ldx)
+        dinv = rec[m * ldx:m * ldx + s8]
+        Ld = rec[m * ldx + 2 * s8:].reshape(s8, 8)
         idx = T["front_idx"][F["idx_off"]:F["idx_off"] + s8 + u8]
         xu = np.zeros((u8, kr))
         for r in range(u8):
             if idx[s8 + r] >= 0:
                 xu[r] = xp[idx[s8 + r]]
-        t = Lp[s8 + u8:, :].T.copy()             # z: s8 x kr
-        t -= Lp[s8:s8 + u8, :].T @ xu
-        L11 = np.tril(Lp[:s8, :], -1) + np.eye(s8)
+        t = (Pn[s8 + u8:, :s8].T - Pn[s8:s8 + u8, :s8].T @ xu) * dinv[:, None]
+        L11 = np.eye(s8)
+        for r in range(s8):
+            for c in range(r):
+                L11[r, c] = Ld[r, c % 8] if r // 8 == c // 8 else Pn[r, c] * dinv[c]
         xo = np.linalg.solve(L11.T, t)
         xp[F["own_base"]:F["own_base"] + s8] = xo
     inv = T["inv_perm"]
