@@ -9,6 +9,7 @@
 #include <iostream>
 #include <map>
 #include <sys/stat.h>
+#include <unistd.h>
 
 namespace msfec {
 
@@ -235,81 +236,81 @@ void owned_range(long long n, int rank, int world, long long &lo, long long &hi)
   hi = ((rank + 1) * n) / world;
 }
 
-namespace {
-int env_int(const char *a, const char *b, const char *c, int dflt) {
-  for (const char *n : {a, b, c})
-    if (n) if (const char *v = std::getenv(n)) return std::atoi(v);
-  return dflt;
+std::string int_to_string(long long value, int digits) {
+  std::string v = std::to_string(value);
+  while ((int)v.size() < digits) v = "0" + v;
+  return v;
 }
-}  // namespace
 
-// Mirrors source/main_ned_rt.cxx:15-117: parse "-p <prm>", run, catch-all.  The fine-grid `*Std` solve and the
-// global coarse solve are outside the hot path; this driver performs the basis build of the
-// rank's cells, reports the "basis initialization and computation" time and writes the coarse element matrices.
-int driver_main(int argc, char **argv, int pairing, const char *name) {
-  try {
-    std::string prm_file;
-    for (int i = 1; i < argc; ++i) {
-      const std::string a = argv[i];
-      if (a == "-p" && i + 1 < argc) prm_file = argv[++i];
-      else if (a == "-h" || a == "--help") { std::cout << "usage: MsFEC_" << name << " -p parameter_file.prm\n"; return 0; }
-      else { std::cerr << "Unknown command line option: " << a << "\nusage: MsFEC_" << name << " -p parameter_file.prm\n"; return 1; }
-    }
-    if (prm_file.empty()) { std::cerr << "usage: MsFEC_" << name << " -p parameter_file.prm\n"; return 1; }
-    const int rank = env_int("OMPI_COMM_WORLD_RANK", "PMI_RANK", "RANK", 0);
-    const int world = env_int("OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "WORLD_SIZE", 1);
-    const int device = env_int("OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "LOCAL_RANK", 0);
-    ParametersMs prm(prm_file, pairing);
-    const long long n_cells = 1LL << (3 * prm.n_refine_global);
-    long long lo, hi;
-    owned_range(n_cells, rank, world, lo, hi);
-    if (rank == 0)
-      std::cout << "MsFEC_" << name << ": " << n_cells << " coarse cells (global refinements " << prm.n_refine_global
-                << "), " << prm.n_refine_local << " local refinements, " << world << " rank(s)\n";
-    auto batch = std::make_shared<BasisBatch>(prm, device);
-    std::vector<int> locals;
-    std::array<std::array<double, 3>, 8> c;
-    for (long long id = lo; id < hi; ++id) { morton_cell(prm.n_refine_global, id, c); locals.push_back(batch->add_cell(c, id)); }
-    const auto t0 = std::chrono::steady_clock::now();
-    batch->build();
-    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    const msfec_stats &st = batch->stats();
-    std::cout << "[rank " << rank << "] " << name << " basis initialization and computation: " << (hi - lo) << " cells in " << sec
-              << " s (device " << st.ms_total << " ms; assemble " << st.ms_assemble << ", lift " << st.ms_lift << ", solve "
-              << st.ms_solve << ", coarse matrices " << st.ms_gram << "; solver " << (st.solver ? "direct" : "MINRES")
-              << ", max its " << st.iterations_max << ", " << st.kernel_launches << " kernel launches)\n";
-    ::mkdir(prm.dirname_output.c_str(), 0755);
-    // "write first basis" (ned_rt_basis.cc:1404-1419): the basis functions of the first coarse cell as VTU
-    if (prm.write_first_basis && rank == 0 && !locals.empty()) {
-      std::vector<double> b0, b1;
-      const int kb = msfec_k(pairing) - (pairing == MSFEC_RT_DQ ? 1 : 0);
-      for (int i = 0; i < kb; ++i) {
-        batch->basis_function(locals[0], i, b0, b1);
-        batch->write_vtu(locals[0], prm.dirname_output + "/basis_" + name + ".cell-" + std::to_string(lo) + ".index-" + std::to_string(i) + ".vtu", b0, b1);
-      }
-      std::cout << "[rank 0] wrote " << kb << " basis VTU files of coarse cell " << lo << " to " << prm.dirname_output << "\n";
-    }
-    const std::string out = prm.dirname_output + "/" + std::string(name) + "_element_matrices.rank" + std::to_string(rank) + ".bin";
-    std::ofstream f(out, std::ios::binary);
-    const int k = batch->k();
-    const long long hdr[4] = {hi - lo, k, lo, pairing};
-    f.write((const char *)hdr, sizeof(hdr));
-    double checksum = 0;
-    for (int i : locals) {
-      f.write((const char *)batch->matrix(i), sizeof(double) * k * k);
-      f.write((const char *)batch->rhs(i), sizeof(double) * k);
-      for (int q = 0; q < k * k; ++q) checksum += batch->matrix(i)[q];
-    }
-    std::printf("[rank %d] wrote %s ; sum of all matrix entries = %.15e\n", rank, out.c_str(), checksum);
-    return 0;
-  } catch (std::exception &exc) {
-    std::cerr << "\n----------------------------------------------------\nException on processing:\n" << exc.what()
-              << "\nAborting!\n----------------------------------------------------\n";
-    return 1;
-  } catch (...) {
-    std::cerr << "\nUnknown exception!\nAborting!\n";
-    return 1;
+std::string CellId::to_string() const {
+  std::string s = "0_" + std::to_string(levels) + ":";
+  for (int l = levels - 1; l >= 0; --l) s += char('0' + ((index >> (3 * l)) & 7));
+  return s;
+}
+
+CoarseCell::CoarseCell(int global_refinements, long long morton_index) : id(morton_index, global_refinements) {
+  morton_cell(global_refinements, morton_index, vertices);
+}
+
+// ---- per-cell classes ------------------------------------------------------------------------------------------
+template <int PAIRING> const char *BasisT<PAIRING>::basis_file_stem() {
+  return PAIRING == MSFEC_Q ? "basis_q" : PAIRING == MSFEC_Q_NED ? "basis_q-ned" : PAIRING == MSFEC_NED_RT ? "basis_ned-rt" : "basis_rt-dq";
+}
+
+// family tag and index inside the family (q_basis.cc:463-468, q_ned_basis.cc:991-1008, ned_rt_basis.cc:1001-1020,
+// rt_dq_basis.cc:952-958)
+template <int PAIRING> std::string BasisT<PAIRING>::basis_file_tag(int n_basis, int &idx) {
+  idx = n_basis;
+  if (PAIRING == MSFEC_Q) return "";
+  if (PAIRING == MSFEC_Q_NED) { if (n_basis < 8) return ".h1"; idx = n_basis - 8; return ".curl"; }
+  if (PAIRING == MSFEC_NED_RT) { if (n_basis < 12) return ".curl"; idx = n_basis - 12; return ".div"; }
+  return ".div";
+}
+
+template <int PAIRING> void BasisT<PAIRING>::run() {
+  char host[256] = "unknown";
+  ::gethostname(host, sizeof(host) - 1);
+  const bool talk = prm_->verbose_basis;
+  // the reference prints this line for every cell (ned_rt_basis.cc:1284-1297, 1421-1427); here under "verbose basis",
+  // the time being this cell's share of the batched device build
+  if (talk)
+    std::cout << "\tSolving for basis in cell   " << cell_.id.to_string() << "   [machine: " << host << " | rank: " << subdomain_
+              << "]   .....";
+  batch_->build();
+  M_ = FullMatrix{batch_->k(), batch_->k(), batch_->matrix(local_)};
+  r_ = Vector{batch_->k(), batch_->rhs(local_)};
+  // set_filename_global (ned_rt_basis.cc:1254-1259)
+  filename_global_ = prm_->filename_output + "." + int_to_string(subdomain_, 5) + ".cell-" + cell_.id.to_string() + ".vtu";
+  // set_output_flag + output_basis (ned_rt_basis.cc:1404-1419): only the first cell writes its basis functions
+  if (prm_->write_first_basis && cell_.id == first_cell_) {
+    ::mkdir(prm_->dirname_output.c_str(), 0755);
+    output_basis();
+  }
+  if (talk) std::cout << "done in   " << batch_->seconds_per_cell() << "   seconds." << std::endl;
+}
+
+template <int PAIRING> void BasisT<PAIRING>::output_basis() {
+  std::vector<double> b0, b1;
+  const int kb = msfec_k(PAIRING) - (PAIRING == MSFEC_RT_DQ ? 1 : 0);
+  for (int n_basis = 0; n_basis < kb; ++n_basis) {
+    int idx = 0;
+    const std::string tag = basis_file_tag(n_basis, idx);
+    const std::string filename = std::string(basis_file_stem()) + tag + "." + int_to_string(subdomain_, 5) + ".cell-" +
+                                 cell_.id.to_string() + ".index-" + int_to_string(idx, 2) + ".vtu";
+    batch_->basis_function(local_, n_basis, b0, b1);
+    batch_->write_vtu(local_, prm_->dirname_output + "/" + filename, b0, b1);
   }
 }
+
+template <int PAIRING> void BasisT<PAIRING>::output_global_solution_in_cell() {
+  std::vector<double> b0, b1;
+  batch_->fine_solution(local_, b0, b1);
+  batch_->write_vtu(local_, prm_->dirname_output + "/" + filename_global_, b0, b1);
+}
+
+template class BasisT<MSFEC_Q>;
+template class BasisT<MSFEC_Q_NED>;
+template class BasisT<MSFEC_NED_RT>;
+template class BasisT<MSFEC_RT_DQ>;
 
 }  // namespace msfec

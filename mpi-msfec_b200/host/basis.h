@@ -53,6 +53,8 @@ class BasisBatch {
   void write_vtu(int cell, const std::string &path, const std::vector<double> &b0, const std::vector<double> &b1);
   const msfec_stats &stats() const { return stats_; }
   int n_cells() const { return (int)ids_.size(); }
+  int pairing() const { return pairing_; }
+  double seconds_per_cell() const { return built_ && !ids_.empty() ? stats_.ms_total * 1e-3 / ids_.size() : 0.0; }
 
  private:
   msfec_ctx *ctx_ = nullptr;
@@ -66,33 +68,86 @@ class BasisBatch {
   void load_layout();
 };
 
-// Per-cell facade with the reference's interface.  Copyable before run(), like the reference
-// (is_copyable, ned_rt_basis.cc:177).
+// Minimal stand-ins for the deal.II return types of the reference's getters (FullMatrix<double>, Vector<double>): views
+// into the batch's host buffers, valid as long as the batch lives.
+struct FullMatrix {
+  int n_rows = 0, n_cols = 0;
+  const double *data = nullptr;
+  double operator()(int i, int j) const { return data[(size_t)i * n_cols + j]; }
+  int m() const { return n_rows; }
+  int n() const { return n_cols; }
+};
+struct Vector {
+  int n = 0;
+  const double *data = nullptr;
+  double operator()(int i) const { return data[i]; }
+  double operator[](int i) const { return data[i]; }
+  int size() const { return n; }
+};
+
+// deal.II CellId of an active cell of the uniformly refined unit cube: "<coarse cell>_<levels>:<child indices>" with the
+// child index of every level = one octal digit of the z-order index, most significant first (CellId::to_string).
+struct CellId {
+  long long index = 0;
+  int levels = 0;
+  CellId() = default;
+  CellId(long long morton_index, int global_refinements) : index(morton_index), levels(global_refinements) {}
+  std::string to_string() const;
+  bool operator<(const CellId &o) const { return index < o.index; }
+  bool operator==(const CellId &o) const { return index == o.index && levels == o.levels; }
+};
+
+// what the reference passes as Triangulation<3>::active_cell_iterator: the 8 vertices (deal.II order) and the id
+struct CoarseCell {
+  std::array<std::array<double, 3>, 8> vertices{};
+  CellId id;
+  CoarseCell() = default;
+  CoarseCell(int global_refinements, long long morton_index);
+};
+
+// Per-cell class with the reference's interface (include/Ned_RT/ned_rt_basis.h:99-153 and the Q / Q_Ned / RT_DQ
+// siblings).  Copyable before run(), like the reference (is_copyable, ned_rt_basis.cc:177): *Multiscale stores the
+// objects by value in a std::map<CellId, XBasis> (ned_rt_global.cc:61-77).  The MPI communicator argument of the
+// reference is replaced by the rank's BasisBatch (one msfec_ctx on one GPU): the first run() of any cell builds the
+// bases of ALL cells registered with the batch in one msfec_build_basis call, later run() calls return at once.
 template <int PAIRING>
 class BasisT {
  public:
-  BasisT(std::shared_ptr<BasisBatch> batch, const std::array<std::array<double, 3>, 8> &corners, long long cell_id,
-         long long first_cell, unsigned local_subdomain)
-      : batch_(std::move(batch)), first_cell_(first_cell), cell_id_(cell_id), subdomain_(local_subdomain) {
-    local_ = batch_->add_cell(corners, cell_id);
+  BasisT(const ParametersMs &parameters_ms, const std::string &parameter_filename, const CoarseCell &global_cell,
+         const CellId &first_cell, unsigned int local_subdomain, std::shared_ptr<BasisBatch> batch)
+      : prm_(&parameters_ms), parameter_filename_(parameter_filename), batch_(std::move(batch)), cell_(global_cell),
+        first_cell_(first_cell), subdomain_(local_subdomain), filename_global_(parameters_ms.filename_output) {
+    local_ = batch_->add_cell(global_cell.vertices, global_cell.id.index);
   }
-  void run() { batch_->build(); }                                              // ned_rt_basis.h:119
-  // k x k row-major, sigma-type coarse DoFs first                             // ned_rt_basis.h:131
-  const double *get_global_element_matrix() const { require(); return batch_->matrix(local_); }
-  const double *get_global_element_rhs() const { require(); return batch_->rhs(local_); }     // :137
-  void set_global_weights(const std::vector<double> &w) { require(); batch_->set_weights(local_, w); }   // :152
+  BasisT(const BasisT &) = default;
+
+  void run();                                                                        // ned_rt_basis.h:119
+  void output_global_solution_in_cell();                                             // :125, ned_rt_basis.cc:1092-1147
+  const FullMatrix &get_global_element_matrix() const { require(); return M_; }      // :131  k x k, sigma-type DoFs first
+  const Vector &get_global_element_rhs() const { require(); return r_; }             // :137
+  const std::string &get_filename_global() const { return filename_global_; }        // :143
+  void set_global_weights(const std::vector<double> &global_weights) {               // :152, ned_rt_basis.cc:1156-1181
+    require(); batch_->set_weights(local_, global_weights);
+  }
+  // not in the reference: the reconstructed fine-scale solution of this cell (what the .vtu is written from)
   void get_global_solution(std::vector<double> &block0, std::vector<double> &block1) { batch_->fine_solution(local_, block0, block1); }
-  std::string get_filename_global() const {                                   // :143, naming of :1254-1259
-    return "fine_solution.cell-" + std::to_string(cell_id_) + ".vtu";
-  }
-  int n_coarse_dofs() const { return batch_->k(); }
+  const CellId &id() const { return cell_.id; }
+  static const char *basis_file_stem();                                              // "basis_ned-rt" ...
+  static std::string basis_file_tag(int n_basis, int &index_in_family);              // ".curl" / ".div" / ".h1" / ""
 
  private:
   void require() const { if (!batch_->built()) throw std::logic_error("basis not built: call run() first"); }
+  void output_basis();                                                               // ned_rt_basis.cc:951-1031
+  const ParametersMs *prm_;
+  std::string parameter_filename_;
   std::shared_ptr<BasisBatch> batch_;
+  CoarseCell cell_;
+  CellId first_cell_;
+  unsigned int subdomain_;
   int local_ = -1;
-  long long first_cell_, cell_id_;
-  unsigned subdomain_;
+  std::string filename_global_;
+  FullMatrix M_;
+  Vector r_;
 };
 
 using QBasis = BasisT<MSFEC_Q>;
@@ -100,12 +155,14 @@ using QNedBasis = BasisT<MSFEC_Q_NED>;
 using NedRTBasis = BasisT<MSFEC_NED_RT>;
 using RTDQBasis = BasisT<MSFEC_RT_DQ>;
 
+std::string int_to_string(long long value, int digits);      // Utilities::int_to_string
+
 // p4est z-order enumeration of the uniformly refined unit cube and the contiguous chunk owned by
 // `rank` (parallel::distributed::Triangulation + is_locally_owned, ned_rt_global.cc:12-15,61-63).
 void morton_cell(int global_refinements, long long index, std::array<std::array<double, 3>, 8> &corners);
 void owned_range(long long n_cells, int rank, int world, long long &lo, long long &hi);
 
-// Shared body of the four executables (source/main_ned_rt.cxx:15-117): "-p file.prm".
+// Shared body of the four executables (source/main_ned_rt.cxx:15-117): "-p file.prm" -> XMultiscale(prm).run().
 int driver_main(int argc, char **argv, int pairing, const char *name);
 
 }  // namespace msfec

@@ -1,0 +1,141 @@
+"""GPU tests of the C++ host side above the C ABI (mpi-msfec_b200/host): the reference-shaped per-cell classes in a
+std::map (source/Ned_RT/ned_rt_global.cc:61-98), and the four MsFEC_* executables end to end -- basis build, coarse
+assembly + solve, weight scatter, norms, VTU / PVTU output with the reference's file names -- on one rank and, when the
+box has two GPUs, on two ranks over NCCL."""
+import os
+import re
+import subprocess
+import sys
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import pytest
+
+import coarse_solve as cs
+from common import ROOT, lib_problem, prm_path, rel_err
+from oracle import msfec_oracle as mo
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(ROOT, "mpi-msfec_b200", "host")
+EXE = {"Q": "MsFEC_Q", "Q_NED": "MsFEC_Q_Ned", "NED_RT": "MsFEC_Ned_RT", "RT_DQ": "MsFEC_RT_DQ"}
+STEM = {"Q": "basis_q", "Q_NED": "basis_q-ned", "NED_RT": "basis_ned-rt", "RT_DQ": "basis_rt-dq"}
+FAMILIES = {"Q": {"": 8}, "Q_NED": {".h1": 8, ".curl": 12}, "NED_RT": {".curl": 12, ".div": 6}, "RT_DQ": {".div": 6}}
+PAIRING = {"Q": 0, "Q_NED": 1, "NED_RT": 2, "RT_DQ": 3}
+
+
+@pytest.fixture(scope="module")
+def host_built(msfec):
+    subprocess.run(["make", "-C", os.path.join(ROOT, "mpi-msfec_b200")], check=True, capture_output=True)
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    return HOST
+
+
+def _small_prm(tmp_path, pairing, L=2, g=2, verbose_basis=False):
+    txt = open(prm_path(pairing)).read()
+    txt = re.sub(r"set local refinements = \d+", f"set local refinements = {L}", txt)
+    txt = re.sub(r"set global refinements = \d+", f"set global refinements = {g}", txt)
+    txt = re.sub(r"set dirname output = \S+", f"set dirname output = {tmp_path}/out", txt)
+    if verbose_basis:
+        txt = txt.replace("set verbose basis = false", "set verbose basis = true")
+    assert "set use direct solver basis = false" in txt           # verbatim flag of the shipped files
+    p = tmp_path / "t.prm"
+    p.write_text(txt)
+    return p, re.search(r"Multiscale method parameters.*?set filename output = (\S+)", txt, re.S).group(1)
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_reference_shaped_classes_in_a_map(host_built, tmp_path, pairing):
+    """host/test_basis_map.cpp: std::map<CellId, XBasis>, copy-construction before run(), run(), getters, weights --
+    bitwise equal to one batched C-ABI call."""
+    prm, _ = _small_prm(tmp_path, pairing, L=2, g=1)
+    r = subprocess.run([os.path.join(host_built, "test_basis_map"), str(PAIRING[pairing]), str(prm)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bitwise" in r.stdout, r.stdout + r.stderr
+
+
+def _run_driver(host_built, pairing, prm, env_extra, nproc=1, port=29611):
+    exe = os.path.join(host_built, EXE[pairing])
+    env = dict(os.environ, **env_extra)
+    if nproc == 1:
+        cmd = [exe, "-p", str(prm)]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), "--no-python", exe, "-p", str(prm)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    return r.stdout
+
+
+def _norms(stdout):
+    line = [l for l in stdout.splitlines() if "Multiscale solution norms" in l][0]
+    return np.array([float(x) for x in re.findall(r"= ([0-9.e+-]+)", line)])
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_driver_end_to_end_single_rank(msfec, host_built, tmp_path, pairing):
+    """MsFEC_* -p file.prm (the reference's CLI) on one rank with the NCCL communicator on: element matrices equal the ctypes
+    path, the C++ coarse solve equals the harness' scipy solve, norms equal the device norms of the same weights, and the
+    output files carry the reference's names (ned_rt_basis.cc:1001-1022, 1254-1259; ned_rt_global.cc:652-700)."""
+    prm, fname = _small_prm(tmp_path, pairing, verbose_basis=True)
+    out = _run_driver(host_built, pairing, prm, {"MSFEC_NCCL": "1"})
+    assert "NCCL communicator over 1 rank(s)" in out and "Outer solver completed." in out
+    assert len(re.findall(r"Solving for basis in cell   0_2:\d\d   \[machine: .* \| rank: 0\]   \.\.\.\.\.done in", out)) == 64
+    d = tmp_path / "out"
+    name = EXE[pairing][6:]
+    raw = np.fromfile(d / f"{name}_element_matrices.rank0.bin", dtype=np.uint8)
+    hdr = raw[:32].view(np.int64)
+    k = int(hdr[1])
+    assert hdr[0] == 64 and hdr[2] == 0
+    el = raw[32:].view(np.float64).reshape(64, k * k + k)
+    cells = mo.morton_cells(2)
+    p = msfec.problem_from_prm(str(prm), pairing)
+    bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(64))
+    assert rel_err(el[:, :k * k], bb.get_global_element_matrix().reshape(64, -1)) < 1e-12
+    assert rel_err(el[:, k * k:], bb.get_global_element_rhs()) < 1e-12
+    # coarse solve: C++ (dense LU at this size) vs scipy
+    wraw = np.fromfile(d / f"{name}_coarse_weights.bin", dtype=np.uint8)
+    w = wraw[16:].view(np.float64).reshape(64, k)
+    w_ref = cs.solve_coarse(pairing, 2, cells, bb.get_global_element_matrix(), bb.get_global_element_rhs())
+    assert rel_err(w, w_ref) < 1e-9
+    # norms printed by the driver == device norms of the same weights through the ctypes path
+    bb.set_global_weights(w)
+    ref = np.sqrt(bb.solution_norms(64).sum(0))
+    got = _norms(out)
+    ref = ref[:len(got)] if pairing != "RT_DQ" else ref[[0, 1, 2]]
+    assert np.allclose(got, ref[:len(got)], rtol=1e-11, atol=0)
+    # files: per-cell solutions, first cell's basis functions, coarse file + two pvtu records
+    sol = sorted(d.glob(f"{fname}.00000.cell-0_2:*.vtu"))
+    assert len(sol) == 64 and (d / f"{fname}.00000.cell-0_2:45.vtu").exists()          # cell 37 = octal 45
+    for fam, cnt in FAMILIES[pairing].items():
+        files = sorted(d.glob(f"{STEM[pairing]}{fam}.00000.cell-0_2:00.index-*.vtu"))
+        assert len(files) == cnt and files[0].name.endswith(".index-00.vtu"), (fam, files)
+    piece = ET.parse(sol[5]).getroot().find("UnstructuredGrid").find("Piece")
+    assert piece.get("NumberOfCells") == "64" and piece.get("NumberOfPoints") == "125"
+    coarse = ET.parse(d / f"{fname}_n_refine-02.0000.vtu").getroot().find("UnstructuredGrid").find("Piece")
+    assert coarse.get("NumberOfCells") == "64"
+    assert [a.get("Name") for a in coarse.find("CellData")][-1] == "subdomain_id"
+    master = ET.parse(d / f"{fname}_n_refine-02.pvtu").getroot().find("PUnstructuredGrid")
+    assert [p_.get("Source") for p_ in master.findall("Piece")] == [f"{fname}_n_refine-02.0000.vtu"]
+    fine = ET.parse(d / f"{fname}_fine_refine-02-02.pvtu").getroot().find("PUnstructuredGrid")
+    assert sorted(p_.get("Source") for p_ in fine.findall("Piece")) == sorted(f.name for f in sol)
+
+
+def test_driver_two_ranks_over_nccl(msfec, host_built, tmp_path):
+    """Two ranks (one per GPU) under torch.distributed.run: the element matrices travel through ncclAllGather, the norms
+    through ncclAllReduce; the printed norms equal the single-rank run to 1e-10 and both ranks write their files."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir()
+    prm1, fname = _small_prm(tmp_path / "a", "NED_RT")
+    prm2, _ = _small_prm(tmp_path / "b", "NED_RT")
+    one = _run_driver(host_built, "NED_RT", prm1, {})
+    two = _run_driver(host_built, "NED_RT", prm2, {"NCCL_DEBUG": "WARN"}, nproc=2)
+    assert "NCCL communicator over 2 rank(s)" in two
+    assert np.allclose(_norms(two), _norms(one), rtol=1e-10, atol=0)
+    d = tmp_path / "b" / "out"
+    assert len(list(d.glob(f"{fname}.00000.cell-*.vtu"))) == 32 and len(list(d.glob(f"{fname}.00001.cell-*.vtu"))) == 32
+    master = ET.parse(d / f"{fname}_n_refine-02.pvtu").getroot().find("PUnstructuredGrid")
+    assert len(master.findall("Piece")) == 2
+    w1 = np.fromfile(tmp_path / "a" / "out" / "Ned_RT_coarse_weights.bin", dtype=np.uint8)[16:].view(np.float64)
+    w2 = np.fromfile(d / "Ned_RT_coarse_weights.bin", dtype=np.uint8)[16:].view(np.float64)
+    assert np.abs(w1 - w2).max() <= 1e-12 * np.abs(w1).max()

@@ -201,49 +201,6 @@ def test_device_pointer_entry(msfec):
     assert rel_err(dM.cpu().numpy(), host.get_global_element_matrix()) < 1e-12
 
 
-def test_cpp_host_driver(msfec, tmp_path):
-    """The C++ MsFEC_Ned_RT executable (host/main_ned_rt.cxx, reference CLI `-p file.prm`) produces the same
-    coarse element matrices as the ctypes path, for 2 'ranks' owning contiguous Morton chunks."""
-    import subprocess
-    from common import prm_path
-    exe = os.path.join(ROOT, "mpi-msfec_b200", "host", "MsFEC_Ned_RT")
-    if not os.path.exists(exe):
-        subprocess.run(["make", "-C", os.path.dirname(exe)], check=True)
-    txt = open(prm_path("NED_RT")).read().replace("set local refinements = 4", "set local refinements = 2")
-    txt = txt.replace("set use direct solver basis = false", "set use direct solver basis = true")
-    txt = txt.replace("set dirname output = data_test-01_NED-RT", f"set dirname output = {tmp_path}/out")
-    prm = tmp_path / "t.prm"
-    prm.write_text(txt)
-    got = {}
-    for rank in (0, 1):
-        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK="0")
-        r = subprocess.run([exe, "-p", str(prm)], env=env, capture_output=True, text=True, timeout=300)
-        assert r.returncode == 0, r.stdout + r.stderr
-        raw = np.fromfile(tmp_path / "out" / f"Ned_RT_element_matrices.rank{rank}.bin", dtype=np.uint8)
-        hdr = raw[:32].view(np.int64)
-        assert hdr[0] == 32 and hdr[1] == 18 and hdr[2] == 32 * rank
-        got[rank] = raw[32:].view(np.float64).reshape(32, 18 * 18 + 18)
-    p = msfec.problem_from_prm(str(prm), "NED_RT")
-    bb = msfec.BasisBuilder(p, device=0).run(mo.morton_cells(2), np.arange(64))
-    M = bb.get_global_element_matrix().reshape(64, -1)
-    both = np.concatenate([got[0], got[1]])
-    assert rel_err(both[:, :324], M) < 1e-12
-    assert rel_err(both[:, 324:], bb.get_global_element_rhs()) < 1e-12
-    # "write first basis = true": 18 ParaView files of the first cell's basis functions
-    import xml.etree.ElementTree as ET
-    files = sorted((tmp_path / "out").glob("basis_Ned_RT.cell-0.index-*.vtu"))
-    assert len(files) == 18
-    piece = ET.parse(files[3]).getroot().find("UnstructuredGrid").find("Piece")
-    assert piece.get("NumberOfCells") == "64" and piece.get("NumberOfPoints") == "125"
-    names = [a.get("Name") for a in piece.find("CellData")]
-    assert names == ["sigma", "u", "div_u"]
-    sig = np.array(piece.find("CellData")[0].text.split(), float).reshape(64, 3)
-    assert np.isfinite(sig).all() and np.abs(sig).max() > 0
-    # error path of the CLI
-    r = subprocess.run([exe, "-x"], capture_output=True, text=True)
-    assert r.returncode == 1
-
-
 @pytest.mark.parametrize("pairing", mo.PAIRINGS)
 def test_reference_prm_configs_full_size(msfec, pairing):
     """BASELINE configs[0..3] at their real size and VERBATIM: the reference's prm_*_test-01.prm (64 coarse cells,
