@@ -58,6 +58,8 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   __shared__ int ch_coff[kMfMaxChildren], ch_ldc[kMfMaxChildren];
   constexpr int NW = NT / 32;
   constexpr int KA = S > 0 ? 2 * S : 1;          // k-steps of a full-width product
+  constexpr int TPS = (S > 0 && S <= 2) ? 8 : 4; // row tiles per step of the contribution update: narrow panels have almost no
+                                                 // MMA work to hide the children gathers behind, so more loads are put in flight
   const int f = M.level_fronts[lf_off + blockIdx.x];
   const MfFront F = M.fronts[f];
   const int cell = blockIdx.y, gcell = cell_lo + cell, g = gcell / kLanes, ln = gcell % kLanes;
@@ -232,7 +234,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
 
   // ---- contribution block: C(I, J) = sum_children C_child - X_I L_J^T.  A warp owns tile columns J (dealt in snake
   // order, long and short columns alternate); per column the A fragments are scaled once and kept in registers (S > 0);
-  // four row tiles per step: the children are gathered through `pinv` straight into the accumulators and the four MMA
+  // TPS row tiles per step: the children are gathered through `pinv` straight into the accumulators and the four MMA
   // chains run interleaved ---------------------------------------------------------------------------------------------
   if (u8 > 0) {
     const int UT = u8 / 8, RT = (u8 + kr) / 8, ldc = u8 + kr;
@@ -256,16 +258,16 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         jc[ci] = ci < nch ? pinv_s[ci * m + colp] : -1;
         cb[ci] = jc[ci] >= 0 ? Cbase + ch_coff[ci] + (size_t)jc[ci] * ch_ldc[ci] : Cbase;
       }
-      for (int I0 = J; I0 < RT; I0 += 4) {
-        double acc[4][2];
+      for (int I0 = J; I0 < RT; I0 += TPS) {
+        double acc[TPS][2];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+        for (int u = 0; u < TPS; ++u) acc[u][0] = acc[u][1] = 0.0;
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
           if (jc[ci] < 0) continue;
           const int *pv = pinv_s + ci * m;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < TPS; ++u) {
             const int I = I0 + u;
             if (I >= RT) continue;
             const int rowp = s8 + I * 8 + 2 * fk;
@@ -279,7 +281,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
           const int jcc = pv[colp];
           if (jcc < 0) continue;
           const double *cbb = Cbase + ch_coff[ci] + (size_t)jcc * ch_ldc[ci];
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < TPS; ++u) {
             const int I = I0 + u;
             if (I >= RT) continue;
             const int rowp = s8 + I * 8 + 2 * fk;
@@ -287,24 +289,24 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
             if (pv[rowp + 1] >= 0 && rowp + 1 >= colp) acc[u][1] += cbb[pv[rowp + 1]];
           }
         }
-        const double *Brow[4];
+        const double *Brow[TPS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) Brow[u] = P + (s8 + min(I0 + u, RT - 1) * 8 + fr) * ldx + fk;
+        for (int u = 0; u < TPS; ++u) Brow[u] = P + (s8 + min(I0 + u, RT - 1) * 8 + fr) * ldx + fk;
         if (S > 0) {
 #pragma unroll
           for (int t = 0; t < KA; ++t) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], af[t], Brow[u][4 * t]);
+            for (int u = 0; u < TPS; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], af[t], Brow[u][4 * t]);
           }
         } else {
           for (int t = 0; t < s8; t += 4) {
             const double a = -Arow[t] * dinv[t + fk];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+            for (int u = 0; u < TPS; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < TPS; ++u)
           if (I0 + u < RT)
             *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + (I0 + u) * 8 + 2 * fk) = make_double2(acc[u][0], acc[u][1]);
       }
@@ -333,9 +335,11 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   double *ts = xu + u8 * ldt;                   // [s8][ldt]  t, then x of the own unknowns
   double *xc = xT + (size_t)cell * k * NP;
   {
+    // the record comes in with cp.async (no registers, no waiting): the gather of x_reached below runs while it is in flight
     const double2 *src = reinterpret_cast<const double2 *>(Lst + (size_t)cell * l_stride + F.l_off);
     double2 *dst = reinterpret_cast<double2 *>(P);
-    for (int i = tid; i < (rec >> 1); i += NT) dst[i] = src[i];
+    for (int i = tid; i < (rec >> 1); i += NT) cp_async16(dst + i, src + i);
+    cp_async_commit();
   }
   for (int j = warp; j < kr; j += NW) {
     if (j < k) {
@@ -347,20 +351,28 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
       for (int r = lane; r < u8; r += 32) xu[r * ldt + j] = 0.0;
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
-  // t(c, j) = (X_z(j, c) - sum_r X21(r, c) x_reached(r, j)) / d_c : 8 x 8 tiles (c-tile, j-tile) over the warps
+  // t(c, j) = (X_z(j, c) - sum_r X21(r, c) x_reached(r, j)) / d_c : 8 x 8 tiles (c-tile, j-tile) over the warps, four
+  // independent accumulator chains over the reached unknowns
   {
     const int CT = s8 / 8, JT = kr / 8;
     for (int tix = warp; tix < CT * JT; tix += NW) {
       const int ct = tix / JT, jt = tix - ct * JT;
-      double a0 = 0.0, a1 = 0.0;
+      double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
       const double *A = P + (s8 + fk) * ldx + ct * 8 + fr;       // A[m = c][k = r] = X21(r, c)
       const double *B = xu + fk * ldt + jt * 8 + fr;             // B[k = r][n = j] = x_reached(r, j)
-      for (int r0 = 0; r0 < u8; r0 += 4) dmma_m8n8k4(a0, a1, A[r0 * ldx], B[r0 * ldt]);
+      int r0 = 0;
+      for (; r0 + 16 <= u8; r0 += 16) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dmma_m8n8k4(a0[q], a1[q], A[(r0 + 4 * q) * ldx], B[(r0 + 4 * q) * ldt]);
+      }
+      for (; r0 < u8; r0 += 4) dmma_m8n8k4(a0[0], a1[0], A[r0 * ldx], B[r0 * ldt]);
+      const double s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
       const int c = ct * 8 + fr, j = jt * 8 + 2 * fk;
       const double di = dinv[c];
-      ts[c * ldt + j] = (P[(s8 + u8 + j) * ldx + c] - a0) * di;
-      ts[c * ldt + j + 1] = (P[(s8 + u8 + j + 1) * ldx + c] - a1) * di;
+      ts[c * ldt + j] = (P[(s8 + u8 + j) * ldx + c] - s0) * di;
+      ts[c * ldt + j + 1] = (P[(s8 + u8 + j + 1) * ldx + c] - s1) * di;
     }
   }
   __syncthreads();
