@@ -93,3 +93,26 @@ def test_morton_partition():
     assert cells[:8, :, :].max() <= 0.5 + 1e-15
     chunks = [mo.partition(64, r, 3) for r in range(3)]
     assert chunks[0][0] == 0 and chunks[-1][1] == 64 and all(chunks[i][1] == chunks[i + 1][0] for i in range(2))
+
+
+@pytest.mark.parametrize("seed", [0, 20261017])
+def test_compiled_cpu_port_matches_oracle(seed):
+    """oracle/msfec_cpu.cpp (the compiled CPU baseline of bench.py, an independent restatement in another language):
+    its exact variant reproduces the Python oracle's Ned_RT element matrices to round-off, its reference-shaped variant
+    (per right-hand side Schur-complement CG + GMRES(ILU(0)) at the reference's 1e-6, ned_rt_basis.cc:637-847) to the
+    accuracy that tolerance gives."""
+    from common import oracle_problem
+    from oracle import msfec_cpu as mc
+    prob = oracle_problem("NED_RT", 2, random_seed=seed)
+    cells = mo.morton_cells(2)
+    sel = np.array([5, 37, 63])
+    ref = [mo.build_basis(prob, cells[c], int(c))[:2] for c in sel]
+    M, r, its = mc.build_basis_ned_rt(prob, cells[sel], sel, "exact", 2)
+    for i in range(3):
+        assert np.abs(M[i] - ref[i][0]).max() <= 1e-12 * np.abs(ref[i][0]).max()
+        assert np.abs(r[i] - ref[i][1]).max() <= 1e-12 * np.abs(ref[i][1]).max()
+    M, r, its = mc.build_basis_ned_rt(prob, cells[sel], sel, "reference", 2)
+    for i in range(3):
+        assert np.abs(M[i] - ref[i][0]).max() <= 1e-5 * np.abs(ref[i][0]).max()
+        assert np.abs(r[i] - ref[i][1]).max() <= 1e-4 * np.abs(ref[i][1]).max()
+    assert (its[:, 0] >= 18).all() and (its[:, 1] > its[:, 0]).all()      # 18 outer solves, inner GMRES inside each S vmult
