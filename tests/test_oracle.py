@@ -116,3 +116,43 @@ def test_compiled_cpu_port_matches_oracle(seed):
         assert np.abs(M[i] - ref[i][0]).max() <= 1e-5 * np.abs(ref[i][0]).max()
         assert np.abs(r[i] - ref[i][1]).max() <= 1e-4 * np.abs(ref[i][1]).max()
     assert (its[:, 0] >= 18).all() and (its[:, 1] > its[:, 0]).all()      # 18 outer solves, inner GMRES inside each S vmult
+
+
+def test_subcomplex_commuting_property():
+    """SURVEY.md s.8(c) invariant 6 (reference doc/pages/mainpage.dox:94-130: the multiscale spaces form a sub-complex).
+    With rough coefficients, to round-off:
+      Ned_RT:  curl of multiscale Nedelec basis m  =  sum_j C[j, m] * multiscale Raviart-Thomas basis j
+      Q_Ned:   grad of multiscale Q1 basis m       =  sum_j G[j, m] * multiscale Nedelec basis j
+    with C, G the curl / gradient incidence of ONE coarse cell in deal.II local order.  This ties the Nedelec and RT
+    sign / orientation conventions, the boundary lifting, the basis-specific volume right-hand sides and the saddle-point
+    solves together -- none of it holds if one convention is off."""
+    import complex_ops as co
+    from common import oracle_problem
+    cells = mo.morton_cells(2)
+    for seed in (0, 20261017):
+        prob = oracle_problem("NED_RT", 2, random_seed=seed)
+        g = mo.fine_grid(prob.n)
+        M, r, X0, X1, cs = mo.build_basis(prob, cells[37], 37)
+        curl_sigma = (co.curl(g) @ X0[:12].T).T                       # [12, nF]
+        pred = co.coarse_incidence(co.curl).T @ X1[12:]               # [12, nF]
+        assert np.abs(curl_sigma).max() > 0
+        assert np.abs(curl_sigma - pred).max() <= 1e-11 * np.abs(curl_sigma).max()
+        prob = oracle_problem("Q_NED", 2, random_seed=seed)
+        M, r, X0, X1, cs = mo.build_basis(prob, cells[37], 37)
+        grad_sigma = (co.gradient(g) @ X0[:8].T).T                    # [8, nE]
+        pred = co.coarse_incidence(co.gradient).T @ X1[8:]            # [8, nE]
+        assert np.abs(grad_sigma - pred).max() <= 1e-11 * np.abs(grad_sigma).max()
+
+
+def test_refinement_self_consistency():
+    """SURVEY.md s.8(c) invariant 5: for a coefficient the fine grids resolve, the coarse element matrices of
+    successive local refinements converge (differences shrink by > 2x per level)."""
+    cells = mo.morton_cells(1)
+    for pairing, rhs in (("Q", "1"), ("NED_RT", "1;2;3")):
+        Ms = []
+        for L in (1, 2, 3, 4 if pairing == "Q" else 3):
+            prob = mo.Problem(pairing=pairing, n_refine_local=L, a_freq=(1, 1, 1), a_alpha=(0.5, 0.4, 0.3), a_rotate=True,
+                              b_expr="1 + 0.5*sin(2*pi*x)", rhs_expr=rhs)
+            Ms.append(mo.build_basis(prob, cells[5], 5)[0])
+        d = [np.abs(Ms[i + 1] - Ms[i]).max() for i in range(2)]
+        assert d[1] < 0.5 * d[0] and d[1] < 0.05 * np.abs(Ms[2]).max(), (pairing, d)
