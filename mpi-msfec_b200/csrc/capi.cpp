@@ -158,8 +158,11 @@ int msfec_problem_from_prm(const char *prm_path, int pairing, msfec_problem *p) 
     p->b_scale = f.get_double(eq + "Diffusion B/scale", 1.0, 0.0001, 10000);
     p->b_alpha = f.get_double(eq + "Diffusion B/alpha", 1.0, 0.0, 10000);
     std::string bexpr = f.get(eq + "Diffusion B/Function expression", "0");
-    // eqn_coeff_B.cc:87-88: the exact-solution runs force the canonical sine expression
-    if (f.get_bool(ms + "use exact solution", false)) bexpr = "scale * (1.0 - alpha * sin(2*pi*frequency*x))";
+    // "use exact solution = true" swaps the right-hand side for RightHandSideExactLin (ned_rt_basis.cc:396-401,
+    // q_ned_basis.cc:394-399) and forces the canonical B (eqn_coeff_B.cc:87-88): the manufactured-solution runs are
+    // outside the hot path and not built, so the file is rejected instead of silently computing another problem
+    if (f.get_bool(ms + "use exact solution", false))
+      return set_error(nullptr, MSFEC_EINVAL, "'use exact solution = true' (manufactured right-hand side) is not supported");
     p->b_expression = dup_string(bexpr);
     p->rhs_expression = dup_string(f.get(eq + "Right-hand side/Function expression", "0"));
     p->rhs_constants = dup_string(f.get(eq + "Right-hand side/Function constants", ""));

@@ -1206,9 +1206,15 @@ void Engine::select_solver() {
   }
   if (want < MSFEC_SOLVER_AUTO || want > MSFEC_SOLVER_MULTIFRONTAL) throw std::invalid_argument("msfec_problem.solver out of range");
   const bool have_band = P_.n_slabs > 0;
-  // contribution blocks of the multifrontal plan are kept per cell between two tree levels; beyond ~64 MB per cell
-  // (4 local refinements) the banded solver is the better fit
-  const bool have_mf = MF_.feasible && (MF_.c_doubles + MF_.l_doubles) * 8 <= ((int64_t)64 << 20);
+  // factor records and contribution blocks of the multifrontal plan live per cell in device memory: the plan is usable
+  // when a minimal sub-batch of 32 cells fits the factorisation budget (48 GB, MSFEC_DIRECT_BAND_GB); MSFEC_MF_MAX_MB
+  // caps the per-cell storage (experiments)
+  double mf_budget_gb = 48.0;
+  if (const char *e = std::getenv("MSFEC_DIRECT_BAND_GB")) mf_budget_gb = std::atof(e);
+  double mf_cap_mb = 1e9;
+  if (const char *e = std::getenv("MSFEC_MF_MAX_MB")) mf_cap_mb = std::atof(e);
+  const double mf_cell_bytes = (double)(MF_.c_doubles + MF_.l_doubles) * 8.0;
+  const bool have_mf = MF_.feasible && mf_cell_bytes * 32.0 <= mf_budget_gb * 1e9 && mf_cell_bytes <= mf_cap_mb * 1e6;
   if (want == MSFEC_SOLVER_MULTIFRONTAL && !MF_.feasible)
     throw std::invalid_argument("multifrontal solver unavailable for this problem size: " + MF_.why);
   if (want == MSFEC_SOLVER_BAND && !have_band) throw std::invalid_argument("direct solver plan unavailable for this problem size");

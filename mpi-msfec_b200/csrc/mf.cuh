@@ -41,9 +41,12 @@ __host__ __device__ inline int mf_record_doubles(int m, int ldx, int s8) { retur
 __host__ __device__ inline size_t mf_fwd_smem_bytes(int m, int ldx, int s8, int nch) {
   return (size_t)mf_record_doubles(m, ldx, s8) * sizeof(double) + (size_t)nch * m * sizeof(int);
 }
-// k_mf_backward: the record, x of the reached unknowns (u8 x (kr + 4)) and t / x of the own unknowns (s8 x (kr + 4))
+// k_mf_backward: the record, a chunk of x of the reached unknowns (<= kMfBwdChunk rows x (kr + 4)) and t / x of the own
+// unknowns (s8 x (kr + 4))
+constexpr int kMfBwdChunk = 64;
 __host__ __device__ inline size_t mf_bwd_smem_bytes(int m, int ldx, int s8, int u8, int kr) {
-  return ((size_t)mf_record_doubles(m, ldx, s8) + (size_t)(u8 + s8) * (kr + 4)) * sizeof(double);
+  const int ch = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
+  return ((size_t)mf_record_doubles(m, ldx, s8) + (size_t)(ch + s8) * (kr + 4)) * sizeof(double);
 }
 
 // grid (fronts of the level, cells of the sub-batch), block NT.  S > 0: every front of the level has s8 = 8 S own
@@ -331,8 +334,9 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   const double *dinv = P + m * ldx;             // [s8]
   const double *Ld = dinv + 2 * s8;             // [s8][8]
   const int rec = mf_record_doubles(m, ldx, s8);
-  double *xu = P + rec;                         // [u8][ldt]  x of the reached unknowns
-  double *ts = xu + u8 * ldt;                   // [s8][ldt]  t, then x of the own unknowns
+  const int CH = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
+  double *xu = P + rec;                         // [CH][ldt]  x of the reached unknowns, one chunk of rows at a time
+  double *ts = xu + CH * ldt;                   // [s8][ldt]  t, then x of the own unknowns
   double *xc = xT + (size_t)cell * k * NP;
   {
     // the record comes in with cp.async (no registers, no waiting): the gather of x_reached below runs while it is in flight
@@ -341,40 +345,45 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
     for (int i = tid; i < (rec >> 1); i += NT) cp_async16(dst + i, src + i);
     cp_async_commit();
   }
-  for (int j = warp; j < kr; j += NW) {
-    if (j < k) {
-      for (int r = lane; r < u8; r += 32) {
-        const int p = M.front_idx[F.idx_off + s8 + r];
-        xu[r * ldt + j] = p >= 0 ? xc[(size_t)j * NP + p] : 0.0;
-      }
-    } else {
-      for (int r = lane; r < u8; r += 32) xu[r * ldt + j] = 0.0;
-    }
-  }
-  cp_async_wait<0>();
-  __syncthreads();
+  const int CT = s8 / 8, JT = kr / 8;
   // t(c, j) = (X_z(j, c) - sum_r X21(r, c) x_reached(r, j)) / d_c : 8 x 8 tiles (c-tile, j-tile) over the warps, four
-  // independent accumulator chains over the reached unknowns
-  {
-    const int CT = s8 / 8, JT = kr / 8;
+  // independent accumulator chains over the reached unknowns of a chunk; partial sums of the chunks meet in ts
+  int r_lo = 0;
+  do {
+    const int nr = min(CH, u8 - r_lo);
+    if (r_lo > 0) __syncthreads();              // the previous chunk has been consumed
+    for (int j = warp; j < kr; j += NW) {
+      if (j < k) {
+        for (int r = lane; r < nr; r += 32) {
+          const int p = M.front_idx[F.idx_off + s8 + r_lo + r];
+          xu[r * ldt + j] = p >= 0 ? xc[(size_t)j * NP + p] : 0.0;
+        }
+      } else {
+        for (int r = lane; r < nr; r += 32) xu[r * ldt + j] = 0.0;
+      }
+    }
+    if (r_lo == 0) cp_async_wait<0>();
+    __syncthreads();
     for (int tix = warp; tix < CT * JT; tix += NW) {
       const int ct = tix / JT, jt = tix - ct * JT;
       double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
-      const double *A = P + (s8 + fk) * ldx + ct * 8 + fr;       // A[m = c][k = r] = X21(r, c)
-      const double *B = xu + fk * ldt + jt * 8 + fr;             // B[k = r][n = j] = x_reached(r, j)
+      const double *A = P + (s8 + r_lo + fk) * ldx + ct * 8 + fr;    // A[m = c][k = r] = X21(r, c)
+      const double *B = xu + fk * ldt + jt * 8 + fr;                 // B[k = r][n = j] = x_reached(r, j)
       int r0 = 0;
-      for (; r0 + 16 <= u8; r0 += 16) {
+      for (; r0 + 16 <= nr; r0 += 16) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) dmma_m8n8k4(a0[q], a1[q], A[(r0 + 4 * q) * ldx], B[(r0 + 4 * q) * ldt]);
       }
-      for (; r0 < u8; r0 += 4) dmma_m8n8k4(a0[0], a1[0], A[r0 * ldx], B[r0 * ldt]);
+      for (; r0 < nr; r0 += 4) dmma_m8n8k4(a0[0], a1[0], A[r0 * ldx], B[r0 * ldt]);
       const double s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
       const int c = ct * 8 + fr, j = jt * 8 + 2 * fk;
-      const double di = dinv[c];
-      ts[c * ldt + j] = (P[(s8 + u8 + j) * ldx + c] - s0) * di;
-      ts[c * ldt + j + 1] = (P[(s8 + u8 + j + 1) * ldx + c] - s1) * di;
+      if (r_lo == 0) { ts[c * ldt + j] = P[(s8 + u8 + j) * ldx + c] - s0; ts[c * ldt + j + 1] = P[(s8 + u8 + j + 1) * ldx + c] - s1; }
+      else { ts[c * ldt + j] -= s0; ts[c * ldt + j + 1] -= s1; }
     }
-  }
+    r_lo += CH;
+  } while (r_lo < u8);
+  __syncthreads();
+  for (int o = tid; o < s8 * kr; o += NT) { const int c = o / kr, j = o - c * kr; ts[c * ldt + j] *= dinv[c]; }
   __syncthreads();
   // L11^T x = t, 8 unknowns at a time, last tile first; below a pivot tile the panel holds X = L D
   for (int p = s8 / 8 - 1; p >= 0; --p) {

@@ -1,5 +1,6 @@
 """Timing of BASELINE.json configs[0..3] (the reference's prm_*_test-01.prm: 64 coarse cells, 4 local
-refinements) through both solver paths, next to the CPU oracle.  Run on a GPU box:
+refinements) through the solvers of the local problems (auto = what the verbatim .prm gets), next to the CPU oracle.
+Run on a GPU box (SOLVERS=auto,band,mf,minres selects; minres on C2 / C3 takes minutes):
     python profiles/config_table.py > gpurun_out/config_table.md
 Parity of these configurations is asserted in tests/test_gpu_parity.py::test_reference_prm_configs_full_size."""
 import importlib.util
@@ -22,14 +23,17 @@ print("| config | pairing | N fine DoFs | k | solver | ms / 64 cells | cells/s |
 print("|---|---|---|---|---|---|---|---|---|---|---|")
 for i, p in enumerate(("Q", "Q_NED", "NED_RT", "RT_DQ")):
     t0 = time.perf_counter(); mo.build_basis(oracle_problem(p, 4), cells[5], 5); cpu = time.perf_counter() - t0
-    for direct in (1, 0):
-        if not direct and p in ("Q_NED", "NED_RT") and os.environ.get("SKIP_SLOW_MINRES"):
+    for solver in os.environ.get("SOLVERS", "auto,band,mf").split(","):
+        try:
+            bb = m.BasisBuilder(lib_problem(m, p, 4, solver=m.SOLVER[solver]), device=0)
+            bb.run(cells)                                  # warm-up (allocations)
+            bb.run(cells)
+        except m.MsfecError as e:
+            print(f"| C{i + 1} {PRM[p]} | {p} | | | {solver} | unavailable: {str(e)[:60]} | | | | | |")
             continue
-        bb = m.BasisBuilder(lib_problem(m, p, 4, use_direct_solver_basis=direct), device=0)
-        bb.run(cells)                                  # warm-up (allocations)
-        bb.run(cells)
         st = bb.stats
         cps = 64 / (st["ms_total"] * 1e-3)
-        print(f"| C{i + 1} {PRM[p]} | {p} | {st['n_fine_dofs']} | {st['k']} | {'block LDL^T' if direct else 'MINRES'} | {st['ms_total']:.1f} | "
+        used = {0: "MINRES", 1: "banded LDL^T", 2: "multifrontal LDL^T"}[st["solver"]]
+        print(f"| C{i + 1} {PRM[p]} | {p} | {st['n_fine_dofs']} | {st['k']} | {solver} -> {used} | {st['ms_total']:.1f} | "
               f"{cps:.1f} | {cps * st['k'] * st['n_fine_dofs']:.3g} | {st['iterations_max']} | {st['residual_max']:.1e} | {cpu:.2f} |")
         bb.close()

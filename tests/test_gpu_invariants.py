@@ -56,13 +56,13 @@ def test_iterative_converges_to_factorisation(msfec):
 
 def test_refinement_self_consistency_on_gpu(msfec):
     """Invariant 5, first half, through the device path: element matrices of successive local refinements converge
-    (Q up to 5 local refinements: multifrontal at 1-3, banded LDL^T at 4-5)."""
+    (Q up to 5 local refinements, whichever factorisation the automatic selection takes)."""
     cells = mo.morton_cells(1)
     Ms = []
     for L in (1, 2, 3, 4, 5):
         p = msfec.make_problem("Q", n_refine_local=L, a_freq=(1, 1, 1), a_alpha=(0.5, 0.4, 0.3), a_rotate=1, rhs_expression=b"1")
         bb = msfec.BasisBuilder(p, device=0).run(cells[5:6], np.array([5]))
-        assert bb.stats["solver"] == (2 if L <= 3 else 1)
+        assert bb.stats["solver"] in (1, 2) and bb.stats["not_converged"] == 0 and bb.stats["residual_max"] < 1e-10
         Ms.append(bb.get_global_element_matrix()[0].copy())
         bb.close()
     d = [np.abs(Ms[i + 1] - Ms[i]).max() for i in range(4)]
@@ -77,7 +77,8 @@ def test_context_reuse_with_fewer_cells(msfec, solver):
     p = lib_problem(msfec, "NED_RT", 2, solver=msfec.SOLVER[solver])
     bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(64))
     M64 = bb.get_global_element_matrix().copy()
-    bb.set_global_weights(np.ones((64, 18)))
+    w = np.random.default_rng(7).standard_normal((64, 18))
+    bb.set_global_weights(w)
     n64 = bb.solution_norms(64)
     bb.run(cells[32:], np.arange(32, 64))
     assert rel_err(bb.get_global_element_matrix(), M64[32:]) < 1e-12
@@ -85,9 +86,9 @@ def test_context_reuse_with_fewer_cells(msfec, solver):
         bb.get_fine_solution(0)                       # weights of the old build are gone
     with pytest.raises(msfec.MsfecError):
         bb.set_global_weights(np.ones((64, 18)))      # cell count of the old build
-    bb.set_global_weights(np.ones((32, 18)))
+    bb.set_global_weights(w[32:])
     n32 = bb.solution_norms(32)
-    assert np.allclose(n32, n64[32:], rtol=1e-12, atol=0)
+    assert np.allclose(n32, n64[32:], rtol=1e-9, atol=0)
     with pytest.raises(msfec.MsfecError):
         bb.get_basis(40, 0)                           # beyond the current build
     with pytest.raises(msfec.MsfecError):

@@ -205,13 +205,19 @@ def test_device_pointer_entry(msfec):
 def test_reference_prm_configs_full_size(msfec, pairing):
     """BASELINE configs[0..3] at their real size and VERBATIM: the reference's prm_*_test-01.prm (64 coarse cells,
     4 local refinements, n = 16, `use direct solver basis = false` as shipped) with no override; the automatic solver
-    selection takes the banded block LDL^T there.  Two cells against the oracle, structure on all."""
+    selection takes the multifrontal LDL^T (chains of narrow fronts at the top separators).  Two cells against the
+    oracle, structure on all; the banded block LDL^T on the same cells agrees to 1e-10."""
     cells = mo.morton_cells(2)
     p = msfec.problem_from_prm(os.path.join(ROOT, "examples", "prm", {"Q": "prm_q_test-01.prm", "Q_NED": "prm_q_ned_test-01.prm",
                                "NED_RT": "prm_ned_rt_test-01.prm", "RT_DQ": "prm_rt_dq_test-01.prm"}[pairing]), pairing)
     assert p.n_refine_local == 4 and p.use_direct_solver_basis == 0 and p.solver == 0
     bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(64))
-    assert bb.stats["solver"] == msfec.SOLVER_STAT["band"] and bb.stats["not_converged"] == 0 and bb.stats["residual_max"] < 1e-10
+    assert bb.stats["solver"] == msfec.SOLVER_STAT["mf"] and bb.stats["not_converged"] == 0 and bb.stats["residual_max"] < 1e-10
+    p.solver = msfec.SOLVER["band"]
+    bb2 = msfec.BasisBuilder(p, device=0).run(cells[:32], np.arange(32))
+    assert bb2.stats["solver"] == msfec.SOLVER_STAT["band"] and bb2.stats["residual_max"] < 1e-10
+    assert rel_err(bb2.get_global_element_matrix(), bb.get_global_element_matrix()[:32]) < 1e-10
+    bb2.close()
     M = bb.get_global_element_matrix()
     assert np.isfinite(M).all()
     k0 = {"Q": 8, "Q_NED": 8, "NED_RT": 12, "RT_DQ": 6}[pairing]

@@ -63,6 +63,14 @@ def test_prm_errors(msfec, tmp_path):
     assert e.value.code == 7
     with pytest.raises(msfec.MsfecError):
         msfec.problem_from_prm(str(tmp_path / "missing.prm"), "Q")
+    # manufactured-solution runs are not built: rejected, not silently changed
+    exact = tmp_path / "exact.prm"
+    txt = open(prm_path("NED_RT")).read()
+    i = txt.index("subsection Multiscale method parameters")
+    exact.write_text(txt[:i] + txt[i:].replace("set use exact solution = false", "set use exact solution = true", 1))
+    with pytest.raises(msfec.MsfecError) as e:
+        msfec.problem_from_prm(str(exact), "NED_RT")
+    assert e.value.code == 1 and "exact solution" in str(e.value)
 
 
 def test_shape_queries(msfec):
@@ -271,8 +279,25 @@ def test_multifrontal_plan_tables(msfec, pairing, L, seed):
 
 
 def test_multifrontal_plan_limits(msfec):
-    """From 4 local refinements on the fronts of the top separators outgrow shared memory: the plan splits them into chains
-    (or reports infeasible) and the engine keeps the banded solver there."""
+    """At 4 local refinements the top separators are split into chains of narrow fronts so that every panel fits one SM's
+    shared memory, and the contribution blocks share an arena about two tree levels deep; at 5 local refinements a Ned_RT
+    front no longer fits at any width and the engine keeps the banded solver."""
     bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 4), device=-1)
-    info = emulate.mf_tables(bb)["info"]
-    assert (info["l_doubles"] + info["c_doubles"]) * 8 > (64 << 20) or not info["feasible"]
+    T = emulate.mf_tables(bb)
+    info = T["info"]
+    assert info["feasible"] and info["n_levels"] > 40
+    assert max(T["smem_fwd"]) <= 227 * 1024 and max(T["smem_bwd"]) <= 227 * 1024
+    total_c = sum((F["u8"] + info["kr"]) * F["u8"] for F in T["fronts"])
+    assert info["c_doubles"] < total_c / 8 and (info["c_doubles"] + info["l_doubles"]) * 8 < 200e6
+    # arena: no two live contribution blocks overlap (a block lives from its level to its parent's level)
+    fr = T["fronts"]
+    spans = [(F["c_off"], F["c_off"] + (F["u8"] + info["kr"]) * F["u8"], F["level"], fr[F["parent"]]["level"] if F["parent"] >= 0 else F["level"])
+             for F in fr if F["u8"]]
+    spans.sort()
+    for i in range(len(spans)):
+        for j in range(i + 1, len(spans)):
+            if spans[j][0] >= spans[i][1]:
+                break
+            assert spans[j][2] > spans[i][3] or spans[i][2] > spans[j][3], (spans[i], spans[j])
+    bb5 = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 5), device=-1)
+    assert not emulate.mf_tables(bb5)["info"]["feasible"]
