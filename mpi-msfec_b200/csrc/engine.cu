@@ -828,29 +828,21 @@ class Engine {
         for (int r = 0; r < T_.NI; ++r)
           if (P_.rhs_dest[r] >= 0)
             for (int j = 0; j < T_.k_solve; ++j) code[P_.rhs_dest[r] + j] = ((r * 32 + j) << 3) | 4;
-        if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_REGION")) fused_region_ = std::max(0, std::min(2, std::atoi(b)));
-        if (fused_region_) {
-          // 32x32 blocks strictly above the diagonal of a block column's own block are never read by the fused-region
-          // schedule (lower-triangular factorisation): code 7 = leave unwritten (15 % of the band for Ned_RT, n = 8)
-          for (int sb = 0; sb < P_.n_slabs; ++sb)
-            for (int c = 0; c < P_.bs[sb]; ++c)
-              for (int r = 0; r < (c / kDP) * kDP; ++r) {
-                int32_t &cd = code[(size_t)P_.col_off[sb] + (size_t)c * P_.ld[sb] + r];
-                if (cd == 0) cd = 7;
-              }
-        }
+        // 32x32 blocks strictly above the diagonal of a block column's own block are never read by the region kernel
+        // (lower-triangular factorisation): code 7 = leave unwritten (15 % of the band for Ned_RT, n = 8)
+        for (int sb = 0; sb < P_.n_slabs; ++sb)
+          for (int c = 0; c < P_.bs[sb]; ++c)
+            for (int r = 0; r < (c / kDP) * kDP; ++r) {
+              int32_t &cd = code[(size_t)P_.col_off[sb] + (size_t)c * P_.ld[sb] + r];
+              if (cd == 0) cd = 7;
+            }
         d_dp_code_ = dev_upload(code);
       }
       for (int v : P_.ld) ldy_ = std::max(ldy_, v);
-      CUDA_OK(cudaFuncSetAttribute(k_direct_update<128, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_smem_bytes<128, 32>(kMaxWindow)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_update_s<64, 64, 8, 4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)update_s_smem<64, 64, 8, 4>()));
       if (const char *b = std::getenv("MSFEC_DIRECT_CHUNK")) direct_chunk_ = std::max(1, std::min(kMaxWindow, std::atoi(b)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_back_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBackGemmSmem));
       CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<32>(kMaxWindow)));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
-      CUDA_OK(cudaFuncSetAttribute(k_direct_trsm<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trsm_smem_bytes<64>(kMaxWindow)));
-      if (const char *b = std::getenv("MSFEC_DIRECT_TRSM_ROWS")) { const int v = std::atoi(b); trsm_rows_ = v == 32 ? 32 : (v == 648 ? 648 : 64); }
-      if (const char *b = std::getenv("MSFEC_DIRECT_FUSED_REGION")) fused_region_ = std::max(0, std::min(2, std::atoi(b)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow, true)));
       CUDA_OK(cudaFuncSetAttribute(k_direct_region_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)region_mma_smem(kMaxWindow, false)));
       if (const char *b = std::getenv("MSFEC_DIRECT_REGION_KEEPX")) region_keepx_max_np_ = std::atoi(b);
@@ -993,12 +985,9 @@ class Engine {
   int *d_dp_inv_ = nullptr, *d_dp_cdest_ = nullptr, *d_dp_cref_ = nullptr, *d_dp_sdest_ = nullptr, *d_dp_kdest_ = nullptr,
       *d_dp_rhs_ = nullptr, *d_dp_code_ = nullptr;
   bool fused_fill_ = true;                   // one-pass zero + fill of the band (k_direct_fill_fused)
-  int fused_region_ = 2;                     // diagonal region of a chunk in one launch: MSFEC_DIRECT_FUSED_REGION = 0 (per-panel
-                                             // launches) | 1 (one warp per cell, FMA) | 2 (one warp per cell, DMMA block products)
   int region_keepx_max_np_ = 6;              // chunks of up to this many panels keep their X blocks in shared memory
                                              // (MSFEC_DIRECT_REGION_KEEPX; wider chunks re-stage L from the band: 3 smem blocks for any
                                              // np, 7 instead of 4 warps/SM at np = 5 -- measured 10.07 vs 9.93 ms, no gain)
-  int trsm_rows_ = 32;                       // k_direct_trsm tile: MSFEC_DIRECT_TRSM_ROWS = 32 (4 warps) | 64 (4 warps) | 648 (64 rows, 8 warps)
   double *d_dp_sval_ = nullptr, *d_dp_kval_ = nullptr;
   // sub-batches can be processed round-robin on several streams ("lanes") with private band storage; measured on
   // B200 this gains nothing (every large kernel fills the GPU and kernels of different streams effectively run
@@ -1008,7 +997,7 @@ class Engine {
   struct DirectLane {
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
-    double *band = nullptr, *diagL = nullptr, *dvec = nullptr, *xT = nullptr, *ybuf = nullptr, *vinv = nullptr;
+    double *band = nullptr, *dvec = nullptr, *xT = nullptr, *ybuf = nullptr, *vinv = nullptr;
   } lane_[kMaxDirectLanes];
   cudaEvent_t ev_ready_ = nullptr, ev_timed_ = nullptr;
   std::vector<cudaEvent_t> ev_upd_;
@@ -1337,8 +1326,8 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
 
 void Engine::free_direct() {
   for (auto &L : lane_) {
-    cudaFree(L.band); cudaFree(L.diagL); cudaFree(L.dvec); cudaFree(L.xT); cudaFree(L.ybuf); cudaFree(L.vinv);
-    L.band = L.diagL = L.dvec = L.xT = L.ybuf = L.vinv = nullptr;
+    cudaFree(L.band); cudaFree(L.dvec); cudaFree(L.xT); cudaFree(L.ybuf); cudaFree(L.vinv);
+    L.band = L.dvec = L.xT = L.ybuf = L.vinv = nullptr;
   }
   direct_sub_ = 0; direct_alloc_ = 0;
 }
@@ -1362,7 +1351,6 @@ void Engine::alloc_direct(int nb) {
   for (int i = 0; i < kDirectLanes; ++i) {
     auto &L = lane_[i];
     CUDA_OK(cudaMalloc(&L.band, (size_t)sub * P_.band_doubles * sizeof(double)));
-    CUDA_OK(cudaMalloc(&L.diagL, (size_t)sub * P_.NP * kDP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.dvec, (size_t)sub * P_.NP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.vinv, (size_t)sub * P_.NP * kDP * sizeof(double)));
     CUDA_OK(cudaMalloc(&L.xT, (size_t)sub * T_.k_solve * P_.NP * sizeof(double)));
@@ -1391,7 +1379,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     const int hi = std::min(nb, lo + sub), nc = hi - lo;
     DirectLane &L = lane_[i_sub % kDirectLanes];
     cudaStream_t stream_ = L.st;                           // everything of this sub-batch goes to its lane
-    double *d_band_ = L.band, *d_diagL_ = L.diagL, *d_dvec_ = L.dvec, *d_xT_ = L.xT, *d_ybuf_ = L.ybuf, *d_vinv_ = L.vinv;
+    double *d_band_ = L.band, *d_dvec_ = L.dvec, *d_xT_ = L.xT, *d_ybuf_ = L.ybuf, *d_vinv_ = L.vinv;
     const int g0 = lo / kLanes, ng = (hi + kLanes - 1) / kLanes - g0;
     // MSFEC_DIRECT_PROFILE=1: per-phase device times of the first sub-batch (events between the launches)
     const bool prof = timed && std::getenv("MSFEC_DIRECT_PROFILE") != nullptr;
@@ -1423,7 +1411,7 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
     // C -= L D L^T over the trapezoid columns [vc_lo, vc_hi) x rows [column, row_hi) of block column s, sources =
     // nq panels from column jsrc (their -L D sits in window-scratch slots 0..nq-1).  strip: one 32-column panel
     // inside the diagonal region of a chunk (small); otherwise everything behind a chunk (the dominant kernel).
-    auto launch_update = [&](int s, int jsrc, int nq, int vc_lo, int vc_hi, bool strip, int row_hi) {
+    auto launch_update = [&](int s, int jsrc, int nq, int vc_lo, int vc_hi, int row_hi) {
       const int ld = P_.ld[s];
       const int c_hi = std::min(vc_hi, P_.front_rows[s]);
       if (c_hi <= vc_lo) return;
@@ -1431,26 +1419,20 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       const double R = row_hi - vc_lo, Cn = c_hi - vc_lo;
       const double flops = 2.0 * kDP * nq * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
       direct_flops_ += flops;
-      const bool tev = timed && !strip && ev_i + 2 <= ev_upd_.size();
+      const bool tev = timed && ev_i + 2 <= ev_upd_.size();
       if (tev) CUDA_OK(cudaEventRecord(ev_upd_[ev_i], stream_));
-      if (strip) {
-        const int T = (row_hi - vc_lo + 127) / 128;
-        k_direct_update<128, 32><<<dim3(1, T, nc), 128, update_smem_bytes<128, 32>(nq), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, 0, vc_lo, c_hi, row_hi, d_ybuf_, ldy_);
-      } else {
-        k_direct_update_s<64, 64, 8, 4, 4><<<dim3(update_s_tiles<64, 64>(ld, vc_lo, c_hi), nc), 128, update_s_smem<64, 64, 8, 4>(), stream_>>>(
-            d_band_, stride, D, s, jsrc, nq, 0, vc_lo, c_hi, d_ybuf_, ldy_);
-        ++direct_update_launches_;
-      }
+      k_direct_update_s<64, 64, 8, 4, 4><<<dim3(update_s_tiles<64, 64>(ld, vc_lo, c_hi), nc), 128, update_s_smem<64, 64, 8, 4>(), stream_>>>(
+          d_band_, stride, D, s, jsrc, nq, 0, vc_lo, c_hi, d_ybuf_, ldy_);
+      ++direct_update_launches_;
       if (tev) { CUDA_OK(cudaEventRecord(ev_upd_[ev_i + 1], stream_)); ev_i += 2; ev_flops.push_back(flops); }
       ++launches_;
-      mark(strip ? "update strip" : "update chunk");
+      mark("update chunk");
     };
     for (int s = 0; s < P_.n_slabs; ++s) {
       const int bs = P_.bs[s], ld = P_.ld[s];
       const int n_panels = bs / kDP;
       // equal CHUNKS of at most direct_chunk_ panels (6 panels -> 3 + 3).  Per chunk:
-      //  (1) factor its diagonal region (rows < 32 c1 only: small, latency-bound launches per 32-column panel),
+      //  (1) factor its diagonal region (one warp per cell, k_direct_region_mma),
       //  (2) solve all rows below the region in one pass on the tensor cores (k_direct_trsm),
       //  (3) apply the chunk to everything behind it: rest of the block column, reached blocks, rhs rows.
       const int n_chunk = (n_panels + direct_chunk_ - 1) / direct_chunk_;
@@ -1458,52 +1440,24 @@ void Engine::solve_direct_batch(int groups, int nb, double kscale, msfec_stats &
       for (int c0 = 0; c0 < n_panels; c0 += chunk) {
         const int c1 = std::min(n_panels, c0 + chunk), np = c1 - c0;
         const int row_hi = c1 * kDP;
-        if (fused_region_) {
-          // one warp per cell factors the whole diagonal region of the chunk
-          if (fused_region_ == 2)
-            if (np <= region_keepx_max_np_)
-              k_direct_region_mma<true><<<nc, 32, region_mma_smem(np, true), stream_>>>(
-                  d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
-            else
-              k_direct_region_mma<false><<<nc, 32, region_mma_smem(np, false), stream_>>>(
-                  d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
-          else
-            k_direct_region<<<(nc + kRegionWarps - 1) / kRegionWarps, 32 * kRegionWarps, 0, stream_>>>(
-                d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, nc, d_dvec_, d_vinv_, d_flag_ + 2);
-          ++launches_;
-          for (int j = c0 + 1; j < c1; ++j) {               // same algorithmic flops as the strip updates below
-            const double R = row_hi - j * kDP, Cn = kDP;
-            direct_flops_ += 2.0 * kDP * (j - c0) * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
-          }
-          mark("region");
-        } else
-        for (int j = c0; j < c1; ++j) {
-          const int j0 = j * kDP, pglob = P_.slab_off[s] + j0;
-          if (j > c0) launch_update(s, c0 * kDP, j - c0, j0, j0 + kDP, true, row_hi);
-          k_direct_diag<<<(nc + 3) / 4, 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, j0, pglob, NP, nc, d_diagL_, d_dvec_, d_vinv_, d_flag_ + 2);
-          ++launches_;
-          mark("diag");
-          const int nrows = row_hi - (j0 + kDP);
-          if (nrows > 0) {
-            k_direct_panel<<<dim3((nrows + 127) / 128, nc), 128, 0, stream_>>>(d_band_, stride, P_.col_off[s], ld, row_hi, j0, pglob, NP, d_diagL_,
-                                                                               d_dvec_, d_ybuf_, j - c0, ldy_);
-            ++launches_;
-            mark("panel");
-          }
-        }
-        if (trsm_rows_ == 648)        // 64 rows, 8 warps
-          k_direct_trsm<64, 8><<<dim3((ld - row_hi + 63) / 64, nc), 256, trsm_smem_bytes<64>(np), stream_>>>(
-            d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
-        else if (trsm_rows_ == 64)
-          k_direct_trsm<64, 4><<<dim3((ld - row_hi + 63) / 64, nc), 128, trsm_smem_bytes<64>(np), stream_>>>(
-            d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+        if (np <= region_keepx_max_np_)
+          k_direct_region_mma<true><<<nc, 32, region_mma_smem(np, true), stream_>>>(
+              d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
         else
-          k_direct_trsm<32, 4><<<dim3((ld - row_hi) / 32, nc), 128, trsm_smem_bytes<32>(np), stream_>>>(
-            d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
+          k_direct_region_mma<false><<<nc, 32, region_mma_smem(np, false), stream_>>>(
+              d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, P_.slab_off[s] + c0 * kDP, NP, d_dvec_, d_vinv_, d_flag_ + 2);
+        ++launches_;
+        for (int j = c0 + 1; j < c1; ++j) {               // flops of the in-region updates
+          const double R = row_hi - j * kDP, Cn = kDP;
+          direct_flops_ += 2.0 * kDP * (j - c0) * (Cn * R - Cn * (Cn - 1) / 2.0) * nc;
+        }
+        mark("region");
+        k_direct_trsm<32, 4><<<dim3((ld - row_hi) / 32, nc), 128, trsm_smem_bytes<32>(np), stream_>>>(
+          d_band_, stride, P_.col_off[s], ld, c0 * kDP, np, row_hi, P_.slab_off[s] + c0 * kDP, NP, d_vinv_, d_dvec_, d_ybuf_, ldy_);
         ++launches_;
         mark("trsm");
         direct_flops_ += (double)(ld - row_hi) * (np * kDP) * ((np + 1) * kDP) * nc;   // 2 * rows * 32^2 * np(np+1)/2
-        launch_update(s, c0 * kDP, np, row_hi, 1 << 30, false, ld);
+        launch_update(s, c0 * kDP, np, row_hi, 1 << 30, ld);
       }
     }
     // backward substitution: chunks in reverse elimination order

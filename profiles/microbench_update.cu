@@ -27,6 +27,11 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
 }  // namespace
 }  // namespace msfec
 #include "../mpi-msfec_b200/csrc/direct.cuh"
+namespace msfec {
+namespace {
+#include "r01_superseded_kernels.cuh"   // k_direct_update<TM, TN> (round-1 variant, out of the product since round 2)
+}  // namespace
+}  // namespace msfec
 
 namespace msfec {
 namespace {
