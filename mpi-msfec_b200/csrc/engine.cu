@@ -931,6 +931,7 @@ class Engine {
   int n_slots_ = 0, R_ = 4;
   // batch buffers
   int batch_groups_ = 0;
+  int auto_cpb_ = 0;                         // cells per resident batch derived from the free device memory (first build)
   double *d_x0_ = nullptr, *d_coef_ = nullptr, *d_fr_ = nullptr, *d_vals_ = nullptr, *d_grhs_ = nullptr, *d_minv_ = nullptr;
   long long *d_gid_ = nullptr;
   double *d_vec_[8]{};   // ra, rb, T, yp, V, wa, wb, x
@@ -1244,6 +1245,7 @@ void Engine::upload_mf() {
 #undef MF_SET_ATTR
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
+  CUDA_OK(cudaFuncSetAttribute(k_mf_backward<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
   for (auto &ev : ev_mf_) CUDA_OK(cudaEventCreate(&ev));
 }
 
@@ -1309,10 +1311,13 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
     CUDA_OK(cudaEventRecord(mf_marks_[mf_marks_used_ + 1], stream_));
     for (int l = MF_.n_levels - 1; l >= 0; --l) {
       const int nfl = MF_.level_off[l + 1] - MF_.level_off[l];
-      if (MF_.smem_bwd[l] <= 112 * 1024)
+      // as in the forward pass: the fewer fronts fit an SM, the more warps each gets
+      if (MF_.smem_bwd[l] <= 56 * 1024)
         k_mf_backward<128><<<dim3(nfl, nc), 128, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
-      else
+      else if (MF_.smem_bwd[l] <= 112 * 1024)
         k_mf_backward<256><<<dim3(nfl, nc), 256, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
+      else
+        k_mf_backward<512><<<dim3(nfl, nc), 512, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
     }
     CUDA_OK(cudaEventRecord(mf_marks_[mf_marks_used_ + 2], stream_));
     mf_marks_used_ += 3;
@@ -1541,8 +1546,9 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   H_last_ = H;
   const double h = H / T_.n;
   const double kscale = std::pow(h, T_.k_h_exponent), f1scale = std::pow(H, T_.f1_H_exponent);
-  int cpb = spec_.p.cells_per_batch;
+  int cpb = spec_.p.cells_per_batch > 0 ? spec_.p.cells_per_batch : auto_cpb_;
   if (cpb <= 0) {
+    // once per context (cudaMemGetInfo takes driver locks; repeated builds re-use the answer)
     // resident batch from the free device memory: coefficient samples, slot values, Krylov / rhs / solution vectors and
     // Y = A Z per cell; at most a third of what is free (the factorisations allocate their own storage), <= 4096 cells
     size_t free_b = 0, total_b = 0;
@@ -1551,6 +1557,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     const double per_cell = 8.0 * ((double)T_.nC * (56 + 8 * T_.rhs_ncomp) + n_slots_ + T_.asm_rhs.n_slots + n_vec * T_.NI + (double)T_.NF * T_.k_gram);
     const double reusable = (double)batch_groups_ * kLanes * per_cell;   // buffers of an earlier build are reused
     cpb = (int)std::min(4096.0, std::max(32.0, std::floor(((double)free_b + reusable) / 3.0 / per_cell / 32.0) * 32.0));
+    auto_cpb_ = cpb;
   }
   const int batch_cells = std::min(n_cells, (cpb + kLanes - 1) / kLanes * kLanes);
   alloc_batch((batch_cells + kLanes - 1) / kLanes);
