@@ -388,6 +388,7 @@ int msfec_debug_table(const msfec_ctx *ctx, const char *name, void *out, size_t 
   else if (n == "mf.perm") iv = &mf.perm; else if (n == "mf.inv_perm") iv = &mf.inv_perm;
   else if (n == "mf.level_off") iv = &mf.level_off; else if (n == "mf.level_fronts") iv = &mf.level_fronts;
   else if (n == "mf.smem_fwd") iv = &mf.smem_fwd; else if (n == "mf.smem_bwd") iv = &mf.smem_bwd;
+  else if (n == "mf.smem_fwd_st") iv = &mf.smem_fwd_st; else if (n == "mf.rt_max") iv = &mf.rt_max;
   std::vector<double> plan_info;
   if (n == "mf.info") {
     plan_info = {mf.feasible ? 1.0 : 0.0, (double)mf.kr, (double)mf.NP, (double)mf.n_levels, (double)mf.l_doubles,

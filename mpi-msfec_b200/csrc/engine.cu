@@ -973,6 +973,9 @@ class Engine {
   std::vector<cudaEvent_t> mf_marks_;        // 3 events per sub-batch: before forward, between, after backward
   size_t mf_marks_used_ = 0;
   long mf_launches_ = 0;
+  int mf_nbuf_ = 0;
+  bool mf_staged_all_ = false;               // MSFEC_MF_STAGED=2: also the levels whose fronts own an SM (measured slower)
+  bool mf_staged_ = true;                    // forward kernel streams the children's blocks (MSFEC_MF_STAGED=0: element gathers)
   // banded direct solver
   bool use_direct_ = false;
   int direct_sub_ = 0;                       // cells per direct sub-batch (step; multiple of 32)
@@ -1238,11 +1241,20 @@ void Engine::upload_mf() {
     }
     if (std::getenv("MSFEC_MF_GENERIC") == nullptr && w > 0 && w / 8 <= 6) mf_level_S_[l] = w / 8;
   }
-#define MF_SET_ATTR(NT, MINB, S) CUDA_OK(cudaFuncSetAttribute(k_mf_forward<NT, MINB, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
+  for (int v : MF_.smem_fwd_st) max_f = std::max(max_f, std::min(v, 231424));
+#define MF_SET_ATTR(NT, MINB, S)                                                                                                   \
+  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<NT, MINB, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));             \
+  CUDA_OK(cudaFuncSetAttribute(k_mf_forward<NT, MINB, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
 #define MF_SET_ATTR_ALL(S) MF_SET_ATTR(128, 6, S) MF_SET_ATTR(256, 2, S) MF_SET_ATTR(512, 1, S)
   MF_SET_ATTR_ALL(0) MF_SET_ATTR_ALL(1) MF_SET_ATTR_ALL(2) MF_SET_ATTR_ALL(3) MF_SET_ATTR_ALL(4) MF_SET_ATTR_ALL(5) MF_SET_ATTR_ALL(6)
 #undef MF_SET_ATTR_ALL
 #undef MF_SET_ATTR
+  mf_staged_ = true;
+  if (const char *e = std::getenv("MSFEC_MF_NBUF")) mf_nbuf_ = std::min(8, std::max(2, std::atoi(e)));
+#ifdef MSFEC_MF_PHASE_SWITCHES
+  if (const char *e = std::getenv("MSFEC_MF_DBG")) { const int v = std::atoi(e); CUDA_OK(cudaMemcpyToSymbol(g_mf_dbg, &v, sizeof(int))); }
+#endif
+  if (const char *e = std::getenv("MSFEC_MF_STAGED")) { mf_staged_ = std::atoi(e) != 0; mf_staged_all_ = std::atoi(e) == 2; }
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
   CUDA_OK(cudaFuncSetAttribute(k_mf_backward<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_b));
@@ -1260,7 +1272,7 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
   // cells per sub-batch from a memory budget for factor + contribution storage (default 48 GB), multiple of 32
   double budget_gb = 48.0;
   if (const char *e = std::getenv("MSFEC_DIRECT_BAND_GB")) budget_gb = std::atof(e);
-  const double per_cell = 8.0 * ((double)MF_.l_doubles + (double)MF_.c_doubles + (double)k * NP);
+  const double per_cell = 8.0 * ((double)MF_.l_doubles + (double)MF_.c_doubles + (double)MF_.kr * NP);
   long sub = std::max(32L, (long)(budget_gb * 1e9 / per_cell) / 32 * 32);
   if (const char *e = std::getenv("MSFEC_MF_BATCH")) sub = std::max(32L, std::atol(e) / 32 * 32);
   sub = std::min<long>(sub, 65535 / 32 * 32);
@@ -1269,7 +1281,7 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
     free_mf();
     CUDA_OK(cudaMalloc(&d_mf_L_, (size_t)need * MF_.l_doubles * sizeof(double)));
     CUDA_OK(cudaMalloc(&d_mf_C_, (size_t)need * std::max<int64_t>(MF_.c_doubles, 1) * sizeof(double)));
-    CUDA_OK(cudaMalloc(&d_mf_xT_, (size_t)need * k * NP * sizeof(double)));
+    CUDA_OK(cudaMalloc(&d_mf_xT_, (size_t)need * MF_.kr * NP * sizeof(double)));
     mf_alloc_ = need;
   }
   CUDA_OK(cudaMemsetAsync(d_vec_[7], 0, (size_t)groups * NI * k * kLanes * sizeof(double), stream_));   // pinned rows stay 0
@@ -1284,17 +1296,42 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
     CUDA_OK(cudaEventRecord(mf_marks_[mf_marks_used_], stream_));
     for (int l = 0; l < MF_.n_levels; ++l) {
       const int nfl = MF_.level_off[l + 1] - MF_.level_off[l];
-      const size_t sm = (size_t)MF_.smem_fwd[l];
-      // threads per front by its shared-memory footprint: small fronts share an SM (6 CTAs of 4 warps), fronts that own an SM
-      // get 16 warps to hide the latency of the children gathers; panel width as a template argument where the level is uniform
-#define MF_LAUNCH(NT, MINB, S)                                                                                                 \
-  k_mf_forward<NT, MINB, S><<<dim3(nfl, nc), NT, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], NI, \
-                                                                k, lo, d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_, (size_t)MF_.c_doubles, d_flag_ + 2)
+      // children streamed through shared memory by bulk copies (mf.cuh, STG) where the ring fits next to the panel and a
+      // tile column has at most 4 row tiles per warp; threads per front by its shared-memory footprint: small fronts share an
+      // SM (6 CTAs of 4 warps), fronts that own an SM get 16 warps; panel width as a template argument where the level is uniform
+      const size_t sm_st = (size_t)MF_.smem_fwd_st[l];
+      const int rt = MF_.rt_max[l];
+      int nt_st = 0;
+      int ldcm = 0;
+      for (int i = MF_.level_off[l]; i < MF_.level_off[l + 1]; ++i) ldcm = std::max(ldcm, MF_.fronts[MF_.level_fronts[i]].ldc_max);
+      // measured (profiles/r02_mf_kernels.md): the streamed variant wins where several fronts share an SM and a staged column is
+      // at least 512 bytes (C5 level 1: -16 %); fronts that own an SM lose the overlap between CTAs to the per-stage barriers
+      if (mf_staged_ && sm_st > 0 && (ldcm >= 64 || mf_staged_all_)) {
+        if (sm_st <= 56 * 1024 && rt <= 16) nt_st = 128;
+        else if (mf_staged_all_ && sm_st <= 112 * 1024 && rt <= 32) nt_st = 256;
+        else if (mf_staged_all_ && sm_st <= 231424 && rt <= 64) nt_st = 512;
+      }
+      // ring depth: as many stage buffers as fit next to the CTAs that share the SM (MSFEC_MF_NBUF: fixed depth, experiments)
+      int nbuf = kMfStageBufs;
+      size_t sm = (size_t)MF_.smem_fwd[l];
+      if (nt_st) {
+        const size_t per_buf = (size_t)8 * ldcm * sizeof(double);
+        if (mf_nbuf_ > 0) nbuf = mf_nbuf_;
+        while (nbuf > 2 && sm_st + (nbuf - 2) * per_buf > 231424) --nbuf;
+        sm = sm_st + (size_t)(nbuf - kMfStageBufs) * per_buf;
+      }
+#define MF_LAUNCH(NT, MINB, S, STG)                                                                                            \
+  k_mf_forward<NT, MINB, S, STG><<<dim3(nfl, nc), NT, sm, stream_>>>(mf_.dev, MF_.level_off[l], d_vals_, n_slots_, kscale, d_vec_[2], \
+                                                                     NI, k, lo, d_mf_L_, (size_t)MF_.l_doubles, d_mf_C_,       \
+                                                                     (size_t)MF_.c_doubles, d_flag_ + 2, nbuf)
 #define MF_LAUNCH_S(S)                                                     \
   do {                                                                     \
-    if (sm <= 56 * 1024) MF_LAUNCH(128, 6, S);                             \
-    else if (sm <= 112 * 1024) MF_LAUNCH(256, 2, S);                       \
-    else MF_LAUNCH(512, 1, S);                                             \
+    if (nt_st == 128) MF_LAUNCH(128, 6, S, true);                          \
+    else if (nt_st == 256) MF_LAUNCH(256, 2, S, true);                     \
+    else if (nt_st == 512) MF_LAUNCH(512, 1, S, true);                     \
+    else if (sm <= 56 * 1024) MF_LAUNCH(128, 6, S, false);                 \
+    else if (sm <= 112 * 1024) MF_LAUNCH(256, 2, S, false);                \
+    else MF_LAUNCH(512, 1, S, false);                                      \
   } while (0)
       switch (mf_level_S_[l]) {
         case 1: MF_LAUNCH_S(1); break;
@@ -1323,7 +1360,7 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
     mf_marks_used_ += 3;
     mf_launches_ += 2 * MF_.n_levels;
     launches_ += 2 * MF_.n_levels;
-    k_direct_scatter_x<<<dim3(NP / kDP, (nc + kLanes - 1) / kLanes), dim3(kLanes, 8), 0, stream_>>>(NP, NI, k, mf_.inv_perm, d_mf_xT_, lo, nc, d_vec_[7]);
+    k_mf_scatter_x<<<dim3(NP / 4, (nc + kLanes - 1) / kLanes), dim3(kLanes, 8), 0, stream_>>>(NP, NI, k, MF_.kr, mf_.inv_perm, d_mf_xT_, lo, nc, d_vec_[7]);
     ++launches_;
   }
   launch_residual_check(groups, kscale, MF_.pinned_row);

@@ -29,7 +29,17 @@ struct MfDev {
   int kr, NP;
 };
 
+// Phase switches for cost attribution (profiles/tools/phase_cost.sh; results in profiles/r02_mf_kernels.md): compiled in only
+// with -DMSFEC_MF_PHASE_SWITCHES, the production library carries none of it.
+#ifdef MSFEC_MF_PHASE_SWITCHES
+__device__ int g_mf_dbg = 0;
+#define MF_DBG_LOAD() const int dbg = g_mf_dbg
+#else
+#define MF_DBG_LOAD() constexpr int dbg = 0
+#endif
 constexpr int kMfMaxChildren = 8;
+constexpr int kMfMaxStageBufs = 8;
+constexpr int kMfFastChildren = 2;   // children handled by the unrolled gather of the contribution update
 
 // Per-front record in the factor storage (written by k_mf_forward, read by k_mf_backward): the shared-memory image of
 // the forward kernel, copied verbatim (one flat coalesced copy each way, no index arithmetic):
@@ -41,6 +51,43 @@ __host__ __device__ inline int mf_record_doubles(int m, int ldx, int s8) { retur
 __host__ __device__ inline size_t mf_fwd_smem_bytes(int m, int ldx, int s8, int nch) {
   return (size_t)mf_record_doubles(m, ldx, s8) * sizeof(double) + (size_t)nch * m * sizeof(int);
 }
+// k_mf_forward with staged children (STG): the record, kMfStageBufs stage buffers of 8 child columns (ldc_max doubles each),
+// the children's inverse maps, one presence flag per (tile column of the front, child)
+__host__ __device__ inline size_t mf_fwd_st_smem_bytes(int m, int ldx, int s8, int u8, int nch, int ldc_max) {
+  const size_t flags = ((size_t)((s8 + u8) / 8) * nch + 7) / 8 * 8;
+  return ((size_t)mf_record_doubles(m, ldx, s8) + (size_t)kMfStageBufs * 8 * ldc_max) * sizeof(double) + (size_t)nch * m * sizeof(int) + flags;
+}
+
+// ---- mbarrier / bulk asynchronous copy (TMA, 1-D) primitives -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t ok;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
+// global -> shared, completion counted in bytes on an mbarrier (16-byte aligned addresses, size a multiple of 16)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// shared -> global as one bulk group
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // k_mf_backward: the record, a chunk of x of the reached unknowns (<= kMfBwdChunk rows x (kr + 4)) and t / x of the own
 // unknowns (s8 x (kr + 4))
 constexpr int kMfBwdChunk = 64;
@@ -52,17 +99,26 @@ __host__ __device__ inline size_t mf_bwd_smem_bytes(int m, int ldx, int s8, int 
 // grid (fronts of the level, cells of the sub-batch), block NT.  S > 0: every front of the level has s8 = 8 S own
 // columns (compile-time panel width: the k-loops unroll and the A fragments of a tile column stay in registers);
 // S = 0: run-time width.
-template <int NT, int MINB, int S>
+// STG: the children's contribution blocks are not gathered element by element from global memory (a dependent round trip to
+// HBM per step: 55-60 % of the stall samples of the levels above the leaves) but STREAMED: one elected thread issues 1-D bulk
+// copies (cp.async.bulk, the TMA unit) of the child columns that fall into one 8-column tile column of this front, one stage
+// = (tile column, child), kMfStageBufs stages in flight, completion on an mbarrier per buffer.  All warps work on the same
+// tile column (row tiles dealt round-robin), pick their entries out of the staged columns through `pinv`, and release the
+// buffer with the barrier that ends the stage.  The first stages are in flight while the panel is assembled and factored.
+template <int NT, int MINB, int S, bool STG>
 __global__ void __launch_bounds__(NT, MINB)
 k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, double kscale,
              const double *__restrict__ b, int NI, int k, int cell_lo, double *__restrict__ Lst, size_t l_stride,
-             double *__restrict__ Cst, size_t c_stride, int *__restrict__ bad) {
+             double *__restrict__ Cst, size_t c_stride, int *__restrict__ bad, int nbuf) {
   extern __shared__ __align__(16) double mf_smem[];
   __shared__ int ch_coff[kMfMaxChildren], ch_ldc[kMfMaxChildren];
+  __shared__ __align__(8) unsigned long long full_bar[kMfMaxStageBufs];
   constexpr int NW = NT / 32;
   constexpr int KA = S > 0 ? 2 * S : 1;          // k-steps of a full-width product
   constexpr int TPS = (S > 0 && S <= 2) ? 8 : 4; // row tiles per step of the contribution update: narrow panels have almost no
                                                  // MMA work to hide the children gathers behind, so more loads are put in flight
+  constexpr int TW = 4;                          // STG: row tiles of one tile column per warp (launch: row tiles <= TW * NW)
+  MF_DBG_LOAD();
   const int f = M.level_fronts[lf_off + blockIdx.x];
   const MfFront F = M.fronts[f];
   const int cell = blockIdx.y, gcell = cell_lo + cell, g = gcell / kLanes, ln = gcell % kLanes;
@@ -75,25 +131,82 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   double *dinv = P + m * ldx;                   // [s8]       1 / d
   double *dval = dinv + s8;                     // [s8]       d
   double *Ld = dval + s8;                       // [s8][8]    unit-lower factors of the 8 x 8 pivot tiles
-  int *pinv_s = reinterpret_cast<int *>(Ld + 8 * s8);   // [nch][m]
+  const int ldcm = STG ? F.ldc_max : 0;
+  double *stg = Ld + 8 * s8;                    // STG: [kMfStageBufs][8][ldcm]  staged child columns
+  int *pinv_s = reinterpret_cast<int *>(stg + (STG ? nbuf : 0) * 8 * ldcm);   // [nch][m]
+  unsigned char *has = reinterpret_cast<unsigned char *>(pinv_s + nch * m);   // STG: [(s8 + u8) / 8][nch]
   const int rec2 = mf_record_doubles(m, ldx, s8) >> 1;
+  const double *Cbase = Cst + (size_t)cell * c_stride;
+  const int TC = (s8 + u8) / 8;
+
+  // STG: issue stage (T, ci) into buffer `buf`: the child columns that map into tile column T, each from its (even) diagonal row
+  // to the end (lower triangle + rhs rows), 16-byte aligned on both sides
+  auto issue_stage = [&](int T, int ci, int buf) {      // threads 0 .. 7: one child column each
+    const int ldc = ch_ldc[ci];
+    const double *Cc = Cbase + ch_coff[ci];
+    uint32_t bytes = 0;
+    const int c = tid;
+    const int jc = pinv_s[ci * m + T * 8 + c];
+    if (jc >= 0) {
+      const int j0 = jc & ~1;
+      bytes = (uint32_t)(ldc - j0) * sizeof(double);
+      bulk_g2s(stg + (size_t)(buf * 8 + c) * ldcm, Cc + (size_t)jc * ldc + j0, bytes, &full_bar[buf]);
+    }
+    mbar_arrive_expect_tx(&full_bar[buf], bytes);
+  };
+  int pT = 0, pci = 0;                          // producer cursor (thread 0): next stage to issue
+  auto issue_next = [&](int buf) {
+    while (pT < TC) {
+      const int T = pT, ci = pci;
+      if (++pci == nch) { pci = 0; ++pT; }
+      if (has[T * nch + ci]) { issue_stage(T, ci, buf); return; }
+    }
+  };
+  int n_stage = 0;                              // stages consumed so far (all threads agree)
 
   // ---- assemble the panel --------------------------------------------------------------------------------
   {
     double2 *P2 = reinterpret_cast<double2 *>(P);
     for (int i = tid; i < rec2; i += NT) P2[i] = make_double2(0.0, 0.0);
   }
+  if (STG) {
+    if (tid < nch) {
+      const MfChild ch = M.children[F.ch_lo + tid];
+      ch_coff[tid] = M.fronts[ch.front].c_off; ch_ldc[tid] = M.fronts[ch.front].u8 + kr;
+    }
+    for (int ci = 0; ci < nch; ++ci) {
+      const int po = M.children[F.ch_lo + ci].pinv_off;
+      for (int i = tid; i < m; i += NT) pinv_s[ci * m + i] = M.pinv[po + i];
+    }
+    if (tid == 0) {
+      for (int bq = 0; bq < nbuf; ++bq) mbar_init(&full_bar[bq], 8);
+      mbar_fence_init();
+    }
+  }
   __syncthreads();
+  if (STG) {
+    for (int t = tid; t < TC * nch; t += NT) {
+      const int T = t / nch, ci = t - T * nch;
+      const int *pv = pinv_s + ci * m + T * 8;
+      bool any = false;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) any = any || pv[c] >= 0;
+      has[t] = any ? 1 : 0;
+    }
+    __syncthreads();
+    if (tid < 8)
+      for (int bq = 0; bq < nbuf; ++bq) issue_next(bq);
+  }
   {
     const double *vc = vals + (size_t)g * n_slots * kLanes + ln;
-    for (int e = F.pe_lo + tid; e < F.pe_hi; e += NT) {
+    for (int e = F.pe_lo + tid; e < ((dbg & 16) ? F.pe_lo : F.pe_hi); e += NT) {
       const int ref = M.pe_ref[e];
       const double v = vc[(size_t)(ref >> 1) * kLanes];
       P[M.pe_dest[e]] = (ref & 1) ? -v : v;
     }
     for (int e = F.pc_lo + tid; e < F.pc_hi; e += NT) P[M.pc_dest[e]] = M.pc_val[e];
     const double *bc = b + (size_t)g * NI * k * kLanes + ln;
-    for (int c = warp; c < s8; c += NW) {
+    for (int c = warp; c < ((dbg & 16) ? 0 : s8); c += NW) {
       const int row = M.own_rows[F.row_off + c];
       if (row < 0) continue;
       for (int j = lane; j < k; j += 32) P[(s8 + u8 + j) * ldx + c] = bc[((size_t)row * k + j) * kLanes];
@@ -102,6 +215,25 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   __syncthreads();
   for (int e = F.ps_lo + tid; e < F.ps_hi; e += NT) P[M.ps_dest[e]] += M.ps_val[e] * kscale;
   __syncthreads();
+  if (STG) {
+    // children, own tile columns of the front: every panel entry collects its child entries from the staged columns
+    for (int q = 0; q < s8 / 8; ++q)
+      for (int ci = 0; ci < nch; ++ci) {
+        if (!has[q * nch + ci]) continue;
+        const int buf = n_stage % nbuf;
+        mbar_wait(&full_bar[buf], (n_stage / nbuf) & 1);
+        const int *pv = pinv_s + ci * m;
+        const double *sb = stg + (size_t)buf * 8 * ldcm;
+        for (int o = q * 64 + tid; o < m * 8; o += NT) {
+          const int c = o & 7, r = o >> 3, col = q * 8 + c;
+          const int jc = pv[col], ir = pv[r];
+          if (jc >= 0 && ir >= 0 && r >= col) P[r * ldx + col] += sb[c * ldcm + ir - (jc & ~1)];
+        }
+        __syncthreads();                         // the buffer is free again (and the panel complete for the next child)
+        if (tid < 8) issue_next(buf);
+        ++n_stage;
+      }
+  } else {
   // children: the leading n_own columns of a child's contribution block belong to this front's own columns
   for (int ci = 0; ci < nch; ++ci) {
     const MfChild ch = M.children[F.ch_lo + ci];
@@ -111,7 +243,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     const double *Cc = Cst + (size_t)cell * c_stride + ccoff;
     const int *cmap = M.cmap + ch.cmap_off;
     for (int i = tid; i < m; i += NT) pinv_s[ci * m + i] = M.pinv[ch.pinv_off + i];
-    for (int j = warp; j < ch.n_own; j += NW) {
+    for (int j = warp; j < ((dbg & 8) ? 0 : ch.n_own); j += NW) {
       const int cj = cmap[j];
       const double *col = Cc + (size_t)j * ldc;
       // eight independent loads in flight per lane
@@ -130,11 +262,12 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     }
     __syncthreads();
   }
+  }
 
   // ---- factor: 8 columns at a time ---------------------------------------------------------------------------
   const int NS = s8 / 8, MT = m / 8;
 #pragma unroll
-  for (int q = 0; q < (S > 0 ? S : NS); ++q) {
+  for (int q = 0; q < ((dbg & 64) ? 0 : (S > 0 ? S : NS)); ++q) {
     const int c0 = q * 8;
     if (q > 0) {
       // left-looking update of tile column q:  P(R, q) -= X(R, 0:c0) L(q, 0:c0)^T   (L = X D^-1), four row tiles of a
@@ -229,20 +362,91 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   }
 
   // ---- factor record -> global: the shared-memory image as it is ---------------------------------------------------
-  {
+  if (STG) {
+    // one bulk copy shared -> global by the TMA unit (the generic-proxy writes of the factorisation are fenced first); nothing
+    // below writes the record region, the issuing thread waits for the read side before the CTA leaves
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      char *dst = reinterpret_cast<char *>(Lst + (size_t)cell * l_stride + F.l_off);
+      const char *src = reinterpret_cast<const char *>(P);
+      const uint32_t total = (uint32_t)rec2 * 16u;
+      for (uint32_t o = 0; o < total; o += 32768u) bulk_s2g(dst + o, src + o, min(32768u, total - o));
+      bulk_commit();
+    }
+  } else {
     double2 *Lo = reinterpret_cast<double2 *>(Lst + (size_t)cell * l_stride + F.l_off);
     const double2 *P2 = reinterpret_cast<const double2 *>(P);
-    for (int i = tid; i < rec2; i += NT) Lo[i] = P2[i];
+    for (int i = tid; i < ((dbg & 4) ? 0 : rec2); i += NT) Lo[i] = P2[i];
+  }
+
+  if (STG) {
+    // ---- contribution block, children staged: all warps on tile column J, warp w takes the row tiles J + w, J + w + NW, ... ----
+    const int UT = u8 / 8, RT = (u8 + kr) / 8, ldc = u8 + kr;
+    double *Co = Cst + (size_t)cell * c_stride + F.c_off;
+    for (int J = 0; J < UT; ++J) {
+      const int colp = s8 + J * 8 + fr;
+      double acc[TW][2];
+#pragma unroll
+      for (int u = 0; u < TW; ++u) acc[u][0] = acc[u][1] = 0.0;
+      for (int ci = 0; ci < nch; ++ci) {
+        if (!has[(s8 / 8 + J) * nch + ci]) continue;
+        const int buf = n_stage % nbuf;
+        mbar_wait(&full_bar[buf], (n_stage / nbuf) & 1);
+        const int *pv = pinv_s + ci * m;
+        const int jc = pv[colp];
+        if (jc >= 0) {
+          const double *sc = stg + (size_t)(buf * 8 + fr) * ldcm - (jc & ~1);
+#pragma unroll
+          for (int u = 0; u < TW; ++u) {
+            const int I = J + warp + u * NW;
+            if (I >= RT) continue;
+            const int rowp = s8 + I * 8 + 2 * fk;
+            const int2 ii = *reinterpret_cast<const int2 *>(pv + rowp);
+            if (ii.x >= 0 && rowp >= colp) acc[u][0] += sc[ii.x];
+            if (ii.y >= 0 && rowp + 1 >= colp) acc[u][1] += sc[ii.y];
+          }
+        }
+        __syncthreads();
+        if (tid < 8) issue_next(buf);
+        ++n_stage;
+      }
+      if (J + warp >= RT) continue;
+      const double *Arow = P + colp * ldx + fk;
+      const double *Brow[TW];
+#pragma unroll
+      for (int u = 0; u < TW; ++u) Brow[u] = P + (s8 + min(J + warp + u * NW, RT - 1) * 8 + fr) * ldx + fk;
+      if (S > 0) {
+#pragma unroll
+        for (int t = 0; t < KA; ++t) {
+          const double a = -Arow[4 * t] * dinv[4 * t + fk];
+#pragma unroll
+          for (int u = 0; u < TW; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][4 * t]);
+        }
+      } else {
+        for (int t = 0; t < s8; t += 4) {
+          const double a = -Arow[t] * dinv[t + fk];
+#pragma unroll
+          for (int u = 0; u < TW; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], a, Brow[u][t]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < TW; ++u) {
+        const int I = J + warp + u * NW;
+        if (I < RT) *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + I * 8 + 2 * fk) = make_double2(acc[u][0], acc[u][1]);
+      }
+    }
+    if (tid == 0) bulk_wait_read();
+    return;
   }
 
   // ---- contribution block: C(I, J) = sum_children C_child - X_I L_J^T.  A warp owns tile columns J (dealt in snake
   // order, long and short columns alternate); per column the A fragments are scaled once and kept in registers (S > 0);
   // TPS row tiles per step: the children are gathered through `pinv` straight into the accumulators and the four MMA
   // chains run interleaved ---------------------------------------------------------------------------------------------
-  if (u8 > 0) {
+  if (u8 > 0 && !(dbg & 32)) {
     const int UT = u8 / 8, RT = (u8 + kr) / 8, ldc = u8 + kr;
     double *Co = Cst + (size_t)cell * c_stride + F.c_off;
-    const double *Cbase = Cst + (size_t)cell * c_stride;
     for (int rnd = 0; rnd * NW < UT; ++rnd) {
       const int J = rnd * NW + ((rnd & 1) ? NW - 1 - warp : warp);
       if (J >= UT) continue;
@@ -253,12 +457,13 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
 #pragma unroll
         for (int t = 0; t < KA; ++t) af[t] = -Arow[4 * t] * dinv[4 * t + fk];
       }
-      // fronts of a dissection tree have at most two children (fast path); more take the loop below
-      int jc[2];
-      const double *cb[2];
+      // fronts of the dissection tree have two children, four where the separators of two leaf pairs were merged into their
+      // parent's (fast path); more take the loop below
+      int jc[kMfFastChildren];
+      const double *cb[kMfFastChildren];
 #pragma unroll
-      for (int ci = 0; ci < 2; ++ci) {
-        jc[ci] = ci < nch ? pinv_s[ci * m + colp] : -1;
+      for (int ci = 0; ci < kMfFastChildren; ++ci) {
+        jc[ci] = (ci < nch && !(dbg & 1)) ? pinv_s[ci * m + colp] : -1;
         cb[ci] = jc[ci] >= 0 ? Cbase + ch_coff[ci] + (size_t)jc[ci] * ch_ldc[ci] : Cbase;
       }
       for (int I0 = J; I0 < RT; I0 += TPS) {
@@ -266,7 +471,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
 #pragma unroll
         for (int u = 0; u < TPS; ++u) acc[u][0] = acc[u][1] = 0.0;
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
+        for (int ci = 0; ci < kMfFastChildren; ++ci) {
           if (jc[ci] < 0) continue;
           const int *pv = pinv_s + ci * m;
 #pragma unroll
@@ -279,7 +484,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
             if (ii.y >= 0 && rowp + 1 >= colp) acc[u][1] += cb[ci][ii.y];
           }
         }
-        for (int ci = 2; ci < nch; ++ci) {
+        for (int ci = kMfFastChildren; ci < nch; ++ci) {
           const int *pv = pinv_s + ci * m;
           const int jcc = pv[colp];
           if (jcc < 0) continue;
@@ -310,14 +515,15 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         }
 #pragma unroll
         for (int u = 0; u < TPS; ++u)
-          if (I0 + u < RT)
+          if (I0 + u < RT && !(dbg & 2))
             *reinterpret_cast<double2 *>(Co + (size_t)(J * 8 + fr) * ldc + (I0 + u) * 8 + 2 * fk) = make_double2(acc[u][0], acc[u][1]);
       }
     }
   }
 }
 
-// grid (fronts of the level, cells of the sub-batch), block NT.  xT[cell][k][NP] holds x in the padded elimination order.
+// grid (fronts of the level, cells of the sub-batch), block NT.  xT[cell][NP][kr] holds x in the padded elimination order
+// (the kr right-hand sides of one unknown are contiguous: the gather of the reached unknowns reads whole 192-byte rows).
 // The front's record comes back into shared memory with one flat copy; t = D^-1 (X_z - X21^T x_reached) runs on the FP64
 // tensor cores (m = own column, n = right-hand side, k = reached unknown), then L11^T x = t tile by tile.
 template <int NT>
@@ -337,7 +543,7 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   const int CH = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
   double *xu = P + rec;                         // [CH][ldt]  x of the reached unknowns, one chunk of rows at a time
   double *ts = xu + CH * ldt;                   // [s8][ldt]  t, then x of the own unknowns
-  double *xc = xT + (size_t)cell * k * NP;
+  double *xc = xT + (size_t)cell * kr * NP;
   {
     // the record comes in with cp.async (no registers, no waiting): the gather of x_reached below runs while it is in flight
     const double2 *src = reinterpret_cast<const double2 *>(Lst + (size_t)cell * l_stride + F.l_off);
@@ -352,15 +558,11 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   do {
     const int nr = min(CH, u8 - r_lo);
     if (r_lo > 0) __syncthreads();              // the previous chunk has been consumed
-    for (int j = warp; j < kr; j += NW) {
-      if (j < k) {
-        for (int r = lane; r < nr; r += 32) {
-          const int p = M.front_idx[F.idx_off + s8 + r_lo + r];
-          xu[r * ldt + j] = p >= 0 ? xc[(size_t)j * NP + p] : 0.0;
-        }
-      } else {
-        for (int r = lane; r < nr; r += 32) xu[r * ldt + j] = 0.0;
-      }
+    // x of the reached unknowns: one row of kr right-hand sides (192 bytes, contiguous in xT[cell][position][kr]) per unknown
+    for (int o = tid; o < nr * kr; o += NT) {
+      const int r = o / kr, j = o - r * kr;
+      const int p = M.front_idx[F.idx_off + s8 + r_lo + r];
+      xu[r * ldt + j] = p >= 0 ? xc[(size_t)p * kr + j] : 0.0;
     }
     if (r_lo == 0) cp_async_wait<0>();
     __syncthreads();
@@ -411,8 +613,32 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
       __syncthreads();
     }
   }
-  for (int j = warp; j < k; j += NW)
-    for (int c = lane; c < s8; c += 32) xc[(size_t)j * NP + F.own_base + c] = ts[c * ldt + j];
+  // own solution: s8 consecutive rows of xT, one contiguous block (columns k .. kr are zero right-hand sides: x = 0)
+  double *xo = xc + (size_t)F.own_base * kr;
+  for (int o = tid; o < s8 * kr; o += NT) { const int c = o / kr, j = o - c * kr; xo[o] = ts[c * ldt + j]; }
+}
+
+// xT[cell][NP][kr] (padded elimination order, per cell) -> x[g][row][k][32] (interior numbering, cell-interleaved), transposed
+// through shared memory so that both sides are coalesced.  cell_lo is a multiple of 32.
+// grid (NP / 4, ceil(cells / 32)), block (32, 8)
+__global__ void __launch_bounds__(256)
+k_mf_scatter_x(int NP, int NI, int k, int kr, const int *__restrict__ inv_perm, const double *__restrict__ xT, int cell_lo,
+               int n_cells, double *__restrict__ x) {
+  constexpr int PC = 4;                                    // positions per block
+  __shared__ double tile[kLanes][PC * 24 + 1];
+  const int lane = threadIdx.x, w = threadIdx.y;
+  const int p0 = blockIdx.x * PC, c0 = blockIdx.y * kLanes;
+  const int g = (cell_lo + c0) / kLanes, W = PC * kr;
+  for (int c = w; c < kLanes; c += 8) {
+    const double *src = xT + ((size_t)(c0 + c) * NP + p0) * kr;
+    for (int o = lane; o < W; o += 32) tile[c][o] = (c0 + c < n_cells) ? src[o] : 0.0;
+  }
+  __syncthreads();
+  for (int o = w; o < PC * k; o += 8) {
+    const int pp = o / k, j = o - pp * k;
+    const int row = inv_perm[p0 + pp];
+    if (row >= 0) x[(((size_t)g * NI + row) * k + j) * kLanes + lane] = tile[lane][pp * kr + j];
+  }
 }
 
 }  // namespace

@@ -25,6 +25,13 @@ size_t mf_smem_forward(const MfFront &f, int n_children, int kr) {
   return mf_record(f) * sizeof(double) + (size_t)n_children * f.m * sizeof(int32_t);
 }
 
+size_t mf_smem_forward_staged(const MfFront &f, int n_children) {
+  // must equal mf_fwd_st_smem_bytes (mf.cuh): the record, kMfStageBufs stage buffers of 8 child columns, the children's inverse
+  // maps, one presence flag per (tile column, child)
+  const size_t flags = ((size_t)((f.s8 + f.u8) / 8) * n_children + 7) / 8 * 8;
+  return (mf_record(f) + (size_t)kMfStageBufs * 8 * f.ldc_max) * sizeof(double) + (size_t)n_children * f.m * sizeof(int32_t) + flags;
+}
+
 size_t mf_smem_backward(const MfFront &f, int kr) {
   // the record + a chunk (<= 64 rows, kMfBwdChunk) of x of the reached unknowns + t / x of the own unknowns; equals
   // mf_bwd_smem_bytes (mf.cuh)
@@ -72,13 +79,23 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget, int min_cells) {
   // RT_DQ: a box whose boundary faces are all still uneliminated is a pure-Neumann problem; every box hands ONE cell
   // DoF up to the separator that joins it with its sibling (same rule as the dissected band plan, topology.cpp).
   const bool defer_u = t.pairing == MSFEC_RT_DQ;
-  std::function<int(const int *, const int *, std::vector<int> &)> rec = [&](const int *lo, const int *hi,
-                                                                              std::vector<int> &idx) -> int {
+  // MSFEC_MF_MERGE=1 (default): relaxed supernodes at the bottom of the tree.  The separator between two leaf boxes is only 8
+  // unknowns wide (Ned_RT) but its front would read and rewrite contribution blocks as large as its parent's; such a box hands
+  // its separator up to the separator of the enclosing box, which then eliminates [sep A | sep B | own] as one supernode (sigma-
+  // type unknowns of all three first, so the no-pivoting argument of DESIGN.md s.3.2 still holds) and has four leaf children.
+  bool merge_small = false;
+  if (const char *e = std::getenv("MSFEC_MF_MERGE")) merge_small = std::atoi(e) != 0;
+  auto cut_axis = [&](const int *lo, const int *hi) {
     int d = -1, best = min_cells;
     for (int a : {2, 1, 0}) if ((hi[a] - lo[a]) / 2 > best) { best = (hi[a] - lo[a]) / 2; d = a; }
     // leaf_x_factor = 2: the last cut (along x) is not made, leaves are boxes of 2 min_cells x min_cells x min_cells fine cells
     // (half as many fronts and one tree level less for ~1.8 x the flops)
     if (d == 0 && (hi[0] - lo[0]) / 2 <= leaf_x_factor * min_cells) d = -1;
+    return d;
+  };
+  std::function<int(const int *, const int *, std::vector<int> &, std::vector<int> *)> rec =
+      [&](const int *lo, const int *hi, std::vector<int> &idx, std::vector<int> *hand_up) -> int {
+    const int d = cut_axis(lo, hi);
     if (d < 0 || idx.empty()) {
       int deferred = -1;
       if (defer_u) {
@@ -95,18 +112,21 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget, int min_cells) {
     for (int i : idx) (all[i].p[d] < mid ? L : all[i].p[d] > mid ? R : Sp).push_back(i);
     int l2[3] = {lo[0], lo[1], lo[2]}, h2[3] = {hi[0], hi[1], hi[2]};
     h2[d] = mid;
-    const int dl = rec(l2, h2, L);
+    const bool left_is_leaf = cut_axis(l2, h2) < 0;
+    const int dl = rec(l2, h2, L, &Sp);
     h2[d] = hi[d]; l2[d] = mid;
-    const int dr = rec(l2, h2, R);
+    const bool right_is_leaf = cut_axis(l2, h2) < 0;
+    const int dr = rec(l2, h2, R, &Sp);
     if (dl >= 0) Sp.push_back(dl);
-    emit(Sp);
+    if (merge_small && hand_up && left_is_leaf && right_is_leaf) hand_up->insert(hand_up->end(), Sp.begin(), Sp.end());
+    else emit(Sp);
     return dr;
   };
   {
     std::vector<int> idx(all.size());
     std::iota(idx.begin(), idx.end(), 0);
     const int lo[3] = {0, 0, 0}, hi[3] = {2 * n, 2 * n, 2 * n};
-    const int left_over = rec(lo, hi, idx);
+    const int left_over = rec(lo, hi, idx, nullptr);
     if (left_over >= 0) {
       nodes.back().rows.push_back(all[left_over].row);
       std::sort(nodes.back().rows.begin(), nodes.back().rows.end());
@@ -285,6 +305,7 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget, int min_cells) {
         } else if (i >= Cf.u8) row = F.s8 + F.u8 + (i - Cf.u8);
         P.cmap.push_back(row);
       }
+      F.ldc_max = std::max(F.ldc_max, Cf.u8 + kr);
       ch.pinv_off = (int)P.pinv.size();
       std::vector<int32_t> inv(F.m, -1);
       for (int i = 0; i < Cf.u8 + kr; ++i) { const int row = P.cmap[ch.cmap_off + i]; if (row >= 0) inv[row] = i; }
@@ -350,8 +371,11 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget, int min_cells) {
   }
   // shared memory per level, flops, algorithmic bytes
   P.smem_fwd.assign(P.n_levels, 0); P.smem_bwd.assign(P.n_levels, 0);
+  P.smem_fwd_st.assign(P.n_levels, 0); P.rt_max.assign(P.n_levels, 0);
   for (auto &F : P.fronts) {
     const int nk = F.ch_hi - F.ch_lo;
+    if (nk > 0) P.smem_fwd_st[F.level] = std::max<int32_t>(P.smem_fwd_st[F.level], (int32_t)std::min<size_t>(mf_smem_forward_staged(F, nk), 1u << 30));
+    P.rt_max[F.level] = std::max<int32_t>(P.rt_max[F.level], (F.u8 + kr) / 8);
     P.smem_fwd[F.level] = std::max<int32_t>(P.smem_fwd[F.level], (int32_t)mf_smem_forward(F, nk, kr));
     P.smem_bwd[F.level] = std::max<int32_t>(P.smem_bwd[F.level], (int32_t)mf_smem_backward(F, kr));
     const double s = F.s8, u = F.u8, rows_below = F.u8 + kr;

@@ -47,6 +47,7 @@ struct MfFront {
   int32_t l_off;          // per-cell factor storage: the front's record [panel m x ldx | 1/d | d | pivot-tile factors], doubles
   int32_t c_off;          // per-cell contribution storage: column-major (u8 + kr) x u8, doubles
   int32_t n_rows_real;    // s + u (diagnostics)
+  int32_t ldc_max;        // largest column length (u8 + kr) of the children's contribution blocks (0: leaf)
 };
 constexpr int kMfFrontFields = sizeof(MfFront) / sizeof(int32_t);
 
@@ -76,6 +77,8 @@ struct MfPlan {
   double bytes_fwd = 0, bytes_bwd = 0;   // algorithmic HBM bytes per cell of k_mf_forward / k_mf_backward
   std::vector<int32_t> smem_fwd;         // per level: dynamic shared memory of the forward kernel (bytes)
   std::vector<int32_t> smem_bwd;         // per level: ... of the backward kernel
+  std::vector<int32_t> smem_fwd_st;      // per level: ... of the forward kernel with staged children (0: level has leaves only)
+  std::vector<int32_t> rt_max;           // per level: most row tiles (u8 + kr) / 8 of a contribution block
 };
 
 // smem_budget: bytes of dynamic shared memory one CTA may use (227 KB on sm_100).  min_cells: edge (fine cells) of the
@@ -85,6 +88,8 @@ MfPlan build_mf_plan(const Topology &t, int smem_budget = 232448 - 1024, int min
 // shared-memory layout of the kernels (bytes), used by both the plan (feasibility) and the launches
 int mf_ldx(int s8);
 size_t mf_smem_forward(const MfFront &f, int n_children, int kr);
+size_t mf_smem_forward_staged(const MfFront &f, int n_children);   // children's columns streamed through a ring (mf.cuh)
+constexpr int kMfStageBufs = 2;   // ring depth of the staged forward kernel
 size_t mf_smem_backward(const MfFront &f, int kr);
 
 }  // namespace msfec

@@ -151,7 +151,7 @@ def emulate_direct(bb, vals, kscale, b):
 
 
 MF_FIELDS = ["s", "s8", "u", "u8", "m", "ldx", "level", "parent", "own_base", "idx_off", "row_off", "pe_lo", "pe_hi",
-             "ps_lo", "ps_hi", "pc_lo", "pc_hi", "ch_lo", "ch_hi", "l_off", "c_off", "n_rows_real"]
+             "ps_lo", "ps_hi", "pc_lo", "pc_hi", "ch_lo", "ch_hi", "l_off", "c_off", "n_rows_real", "ldc_max"]
 
 
 def mf_tables(bb):
@@ -164,7 +164,7 @@ def mf_tables(bb):
              fronts=[dict(zip(MF_FIELDS, row.tolist())) for row in fr],
              children=bb.table("mf.children").reshape(-1, 4))
     for name in ("front_idx", "own_rows", "cmap", "pinv", "pe_dest", "pe_ref", "ps_dest", "ps_val", "pc_dest", "pc_val",
-                 "perm", "inv_perm", "level_off", "level_fronts", "smem_fwd", "smem_bwd"):
+                 "perm", "inv_perm", "level_off", "level_fronts", "smem_fwd", "smem_bwd", "smem_fwd_st", "rt_max"):
         T[name] = bb.table("mf." + name)
     return T
 
