@@ -88,8 +88,8 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// k_mf_backward: the record, a chunk of x of the reached unknowns (<= kMfBwdChunk rows x (kr + 4)) and t / x of the own
-// unknowns (s8 x (kr + 4))
+// k_mf_backward: the record, a chunk of x of the reached unknowns (<= kMfBwdChunk rows x (kr + 4)), t / x of the own
+// unknowns (s8 x (kr + 4)); the positions of the reached unknowns of two chunks sit in static shared memory
 constexpr int kMfBwdChunk = 64;
 __host__ __device__ inline size_t mf_bwd_smem_bytes(int m, int ldx, int s8, int u8, int kr) {
   const int ch = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
@@ -543,28 +543,40 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   const int CH = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
   double *xu = P + rec;                         // [CH][ldt]  x of the reached unknowns, one chunk of rows at a time
   double *ts = xu + CH * ldt;                   // [s8][ldt]  t, then x of the own unknowns
+  __shared__ int idx_s[2 * kMfBwdChunk];        // [2][CH]  padded positions of the reached unknowns, chunk c in half c & 1
   double *xc = xT + (size_t)cell * kr * NP;
   {
-    // the record comes in with cp.async (no registers, no waiting): the gather of x_reached below runs while it is in flight
+    // everything comes in asynchronously (cp.async: no registers, no dependent round trips): first the positions of the reached
+    // unknowns, then the record; the gather of x_reached below is issued as soon as the positions have landed
+    for (int r = tid; r < CH; r += NT) cp_async4(idx_s + r, M.front_idx + F.idx_off + s8 + r);
+    cp_async_commit();
     const double2 *src = reinterpret_cast<const double2 *>(Lst + (size_t)cell * l_stride + F.l_off);
     double2 *dst = reinterpret_cast<double2 *>(P);
     for (int i = tid; i < (rec >> 1); i += NT) cp_async16(dst + i, src + i);
     cp_async_commit();
+    cp_async_wait<1>();
+    __syncthreads();
   }
-  const int CT = s8 / 8, JT = kr / 8;
+  const int CT = s8 / 8, JT = kr / 8, kr2 = kr >> 1;
   // t(c, j) = (X_z(j, c) - sum_r X21(r, c) x_reached(r, j)) / d_c : 8 x 8 tiles (c-tile, j-tile) over the warps, four
   // independent accumulator chains over the reached unknowns of a chunk; partial sums of the chunks meet in ts
-  int r_lo = 0;
+  int r_lo = 0, ib = 0;
   do {
     const int nr = min(CH, u8 - r_lo);
     if (r_lo > 0) __syncthreads();              // the previous chunk has been consumed
-    // x of the reached unknowns: one row of kr right-hand sides (192 bytes, contiguous in xT[cell][position][kr]) per unknown
-    for (int o = tid; o < nr * kr; o += NT) {
-      const int r = o / kr, j = o - r * kr;
-      const int p = M.front_idx[F.idx_off + s8 + r_lo + r];
-      xu[r * ldt + j] = p >= 0 ? xc[(size_t)p * kr + j] : 0.0;
+    // x of the reached unknowns: one row of kr right-hand sides (192 bytes, contiguous in xT[cell][position][kr]) per unknown,
+    // 16 bytes per asynchronous copy, all of them in flight at once
+    for (int o = tid; o < nr * kr2; o += NT) {
+      const int r = o / kr2, q = o - r * kr2;
+      const int p = idx_s[ib * CH + r];
+      double2 *d2 = reinterpret_cast<double2 *>(xu + r * ldt) + q;
+      if (p >= 0) cp_async16(d2, reinterpret_cast<const double2 *>(xc + (size_t)p * kr) + q);
+      else *d2 = make_double2(0.0, 0.0);
     }
-    if (r_lo == 0) cp_async_wait<0>();
+    // the positions of the next chunk travel with this group
+    for (int r = tid; r < min(CH, u8 - r_lo - CH); r += NT) cp_async4(idx_s + (ib ^ 1) * CH + r, M.front_idx + F.idx_off + s8 + r_lo + CH + r);
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     for (int tix = warp; tix < CT * JT; tix += NW) {
       const int ct = tix / JT, jt = tix - ct * JT;
@@ -582,7 +594,7 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
       if (r_lo == 0) { ts[c * ldt + j] = P[(s8 + u8 + j) * ldx + c] - s0; ts[c * ldt + j + 1] = P[(s8 + u8 + j + 1) * ldx + c] - s1; }
       else { ts[c * ldt + j] -= s0; ts[c * ldt + j + 1] -= s1; }
     }
-    r_lo += CH;
+    r_lo += CH; ib ^= 1;
   } while (r_lo < u8);
   __syncthreads();
   for (int o = tid; o < s8 * kr; o += NT) { const int c = o / kr, j = o - c * kr; ts[c * ldt + j] *= dinv[c]; }
@@ -603,13 +615,15 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
     }
     __syncthreads();
     if (c0 > 0) {
-      for (int j = warp; j < kr; j += NW)
-        for (int cp = lane; cp < c0; cp += 32) {
-          double acc = 0.0;
+      // t(cp, j) -= (1 / d_cp) sum_i X(c0 + i, cp) x(c0 + i, j) for the columns before the tile: (cp, j) pairs over all threads,
+      // j fastest (kr is a multiple of 8: the 32 lanes of a warp cover 4 / 3 values of cp, x is read without bank conflicts)
+      for (int o = tid; o < c0 * kr; o += NT) {
+        const int cp = o / kr, j = o - cp * kr;
+        double acc = 0.0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc = fma(P[(c0 + i) * ldx + cp], ts[(c0 + i) * ldt + j], acc);
-          ts[cp * ldt + j] -= acc * dinv[cp];
-        }
+        for (int i = 0; i < 8; ++i) acc = fma(P[(c0 + i) * ldx + cp], ts[(c0 + i) * ldt + j], acc);
+        ts[cp * ldt + j] -= acc * dinv[cp];
+      }
       __syncthreads();
     }
   }

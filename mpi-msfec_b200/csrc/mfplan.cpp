@@ -33,7 +33,7 @@ size_t mf_smem_forward_staged(const MfFront &f, int n_children) {
 }
 
 size_t mf_smem_backward(const MfFront &f, int kr) {
-  // the record + a chunk (<= 64 rows, kMfBwdChunk) of x of the reached unknowns + t / x of the own unknowns; equals
+  // the record + a chunk (<= 64 rows, kMfBwdChunk) of x of the reached unknowns + t / x of the own unknowns ; equals
   // mf_bwd_smem_bytes (mf.cuh)
   return (mf_record(f) + (size_t)(std::min(f.u8, 64) + f.s8) * (kr + 4)) * sizeof(double);
 }
