@@ -198,22 +198,50 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
       for (int bq = 0; bq < nbuf; ++bq) issue_next(bq);
   }
   {
+    // per-cell inputs: slot values and lifted right-hand sides, four entries per thread and pass so that the index loads and
+    // then the value loads of a pass are in flight together (two round trips per pass; one pass covers the leaf fronts)
     const double *vc = vals + (size_t)g * n_slots * kLanes + ln;
-    for (int e = F.pe_lo + tid; e < ((dbg & 16) ? F.pe_lo : F.pe_hi); e += NT) {
-      const int ref = M.pe_ref[e];
-      const double v = vc[(size_t)(ref >> 1) * kLanes];
-      P[M.pe_dest[e]] = (ref & 1) ? -v : v;
+    for (int e0 = F.pe_lo + tid; e0 < ((dbg & 16) ? F.pe_lo : F.pe_hi); e0 += 4 * NT) {
+      int ref[4], dst[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = min(e0 + u * NT, F.pe_hi - 1);
+        ref[u] = M.pe_ref[e]; dst[u] = M.pe_dest[e];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = vc[(size_t)(ref[u] >> 1) * kLanes];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u * NT < F.pe_hi) P[dst[u]] = (ref[u] & 1) ? -v[u] : v[u];
     }
     for (int e = F.pc_lo + tid; e < F.pc_hi; e += NT) P[M.pc_dest[e]] = M.pc_val[e];
     const double *bc = b + (size_t)g * NI * k * kLanes + ln;
-    for (int c = warp; c < ((dbg & 16) ? 0 : s8); c += NW) {
-      const int row = M.own_rows[F.row_off + c];
-      if (row < 0) continue;
-      for (int j = lane; j < k; j += 32) P[(s8 + u8 + j) * ldx + c] = bc[((size_t)row * k + j) * kLanes];
+    const int n_in = (dbg & 16) ? 0 : s8 * k;
+    for (int o0 = tid; o0 < n_in; o0 += 4 * NT) {
+      int row[4], c[4], j[4];
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int o = min(o0 + u * NT, n_in - 1);
+        c[u] = o / k; j[u] = o - c[u] * k;
+        row[u] = M.own_rows[F.row_off + c[u]];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = row[u] >= 0 ? bc[((size_t)row[u] * k + j[u]) * kLanes] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (o0 + u * NT < n_in && row[u] >= 0) P[(s8 + u8 + j[u]) * ldx + c[u]] = v[u];
     }
   }
   __syncthreads();
-  for (int e = F.ps_lo + tid; e < F.ps_hi; e += NT) P[M.ps_dest[e]] += M.ps_val[e] * kscale;
+  for (int e0 = F.ps_lo + tid; e0 < F.ps_hi; e0 += 2 * NT) {
+    const int e1 = e0 + NT;
+    const int d0 = M.ps_dest[e0], d1 = M.ps_dest[min(e1, F.ps_hi - 1)];
+    const double v0 = M.ps_val[e0], v1 = M.ps_val[min(e1, F.ps_hi - 1)];
+    P[d0] += v0 * kscale;
+    if (e1 < F.ps_hi) P[d1] += v1 * kscale;
+  }
   __syncthreads();
   if (STG) {
     // children, own tile columns of the front: every panel entry collects its child entries from the staged columns
@@ -246,7 +274,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     for (int j = warp; j < ((dbg & 8) ? 0 : ch.n_own); j += NW) {
       const int cj = cmap[j];
       const double *col = Cc + (size_t)j * ldc;
-      // eight independent loads in flight per lane
+      // eight independent loads in flight per lane (two columns per pass with sixteen loads measured slower: registers)
       for (int i0 = j + lane; i0 < ldc; i0 += 256) {
         double v[8];
         int ri[8];
