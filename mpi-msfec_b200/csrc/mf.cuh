@@ -493,6 +493,10 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
       for (int ci = 0; ci < kMfFastChildren; ++ci) {
         jc[ci] = (ci < nch && !(dbg & 1)) ? pinv_s[ci * m + colp] : -1;
         cb[ci] = jc[ci] >= 0 ? Cbase + ch_coff[ci] + (size_t)jc[ci] * ch_ldc[ci] : Cbase;
+#ifdef MSFEC_MF_PHASE_SWITCHES
+        if (dbg & 128) cb[ci] = jc[ci] >= 0 ? Cst + ch_coff[ci] + (size_t)jc[ci] * ch_ldc[ci] : Cst;   // every cell reads cell 0's blocks: L2 hits
+        if (dbg & 256) cb[ci] = Cst + (jc[ci] & 7) * 32;                                              // a 2 KB window: L1 hits
+#endif
       }
       for (int I0 = J; I0 < RT; I0 += TPS) {
         double acc[TPS][2];
