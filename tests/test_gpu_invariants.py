@@ -97,3 +97,23 @@ def test_context_reuse_with_fewer_cells(msfec, solver):
     bb.run(cells, np.arange(64))
     assert rel_err(bb.get_global_element_matrix(), M64) < 1e-12
     bb.close()
+
+
+def test_streamed_children_match_gathered_children(msfec, monkeypatch):
+    """k_mf_forward streams the children's contribution blocks of the level-1 fronts through shared memory with bulk copies
+    (cp.async.bulk + mbarrier ring, mf.cuh STG); MSFEC_MF_STAGED=0 gathers them element by element, MSFEC_MF_STAGED=2 streams every
+    level that fits.  All three sum the children in the same order, so the element matrices agree to round-off, and each
+    reproduces the oracle."""
+    cells = mo.morton_cells(2)[:48]
+    ids = np.arange(48)
+    prob = oracle_problem("NED_RT", 3, random_seed=20261017)
+    Mo = mo.build_basis(prob, cells[11], 11)[0]
+    out = {}
+    for mode in ("0", "1", "2"):
+        monkeypatch.setenv("MSFEC_MF_STAGED", mode)
+        bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 3, random_seed=20261017, solver=msfec.SOLVER["mf"]), device=0).run(cells, ids)
+        out[mode] = bb.get_global_element_matrix().copy()
+        assert bb.stats["solver"] == 2 and bb.stats["residual_max"] < 1e-10
+        assert rel_err(out[mode][11], Mo) < 1e-9
+        bb.close()
+    assert rel_err(out["1"], out["0"]) < 1e-12 and rel_err(out["2"], out["0"]) < 1e-12

@@ -228,10 +228,11 @@ def test_reference_prm_configs_full_size(msfec, pairing):
     assert worst < TOL
 
 
-@pytest.mark.parametrize("pairing", ["Q", "RT_DQ"])
+@pytest.mark.parametrize("pairing", ["Q", "RT_DQ", "Q_NED", "NED_RT"])
 def test_minres_full_size(msfec, pairing):
     """The batched MINRES path (msfec_problem.solver = MSFEC_SOLVER_MINRES; the memory fallback of the automatic selection)
-    at n = 16."""
+    at n = 16, i.e. BASELINE configs 1-4 at their shipped size (the mixed H1-H(curl) / H(curl)-H(div) pairings need several
+    thousand iterations with the diagonal preconditioner: 32 cells keep the test short)."""
     cells = mo.morton_cells(2)[:32]
     p = lib_problem(msfec, pairing, 4, solver=msfec.SOLVER["minres"])
     bb = msfec.BasisBuilder(p, device=0).run(cells, np.arange(32))
