@@ -872,7 +872,7 @@ class Engine {
     free_batch(); free_store(); free_direct(); free_mf();
     for (auto &m : mf_marks_) cudaEventDestroy(m);
     for (auto &ev : ev_mf_) if (ev) cudaEventDestroy(ev);
-    cudaFree(mf_.fronts); cudaFree(mf_.children); cudaFree(mf_.front_idx); cudaFree(mf_.own_rows); cudaFree(mf_.cmap); cudaFree(mf_.pinv);
+    cudaFree(mf_.recs); cudaFree(mf_.fronts); cudaFree(mf_.children); cudaFree(mf_.front_idx); cudaFree(mf_.own_rows); cudaFree(mf_.cmap); cudaFree(mf_.pinv);
     cudaFree(mf_.pe_dest); cudaFree(mf_.pe_ref); cudaFree(mf_.ps_dest); cudaFree(mf_.pc_dest); cudaFree(mf_.level_fronts); cudaFree(mf_.inv_perm);
     cudaFree(mf_.ps_val); cudaFree(mf_.pc_val);
     for (auto &ev : ev_upd_) cudaEventDestroy(ev);
@@ -960,7 +960,7 @@ class Engine {
   void solve_mf_batch(int groups, int nb, double kscale);
   void launch_residual_check(int groups, double kscale, int pinned_row);
   struct MfStore {
-    MfFront *fronts = nullptr; MfChild *children = nullptr;
+    MfRec *recs = nullptr; MfFront *fronts = nullptr; MfChild *children = nullptr;
     int *front_idx = nullptr, *own_rows = nullptr, *cmap = nullptr, *pinv = nullptr, *pe_dest = nullptr, *pe_ref = nullptr,
         *ps_dest = nullptr, *pc_dest = nullptr, *level_fronts = nullptr, *inv_perm = nullptr;
     double *ps_val = nullptr, *pc_val = nullptr;
@@ -1226,7 +1226,23 @@ void Engine::upload_mf() {
   mf_.ps_dest = dev_upload(MF_.ps_dest); mf_.ps_val = dev_upload(MF_.ps_val);
   mf_.pc_dest = dev_upload(MF_.pc_dest); mf_.pc_val = dev_upload(MF_.pc_val);
   mf_.level_fronts = dev_upload(MF_.level_fronts); mf_.inv_perm = dev_upload(MF_.inv_perm);
-  mf_.dev = MfDev{mf_.fronts, mf_.children, mf_.front_idx, mf_.own_rows, mf_.cmap, mf_.pinv, mf_.pe_dest, mf_.pe_ref,
+  {
+    // one record per (level, position) with the children's data inline (mf.cuh: MfRec)
+    std::vector<MfRec> recs(MF_.level_fronts.size());
+    for (size_t i = 0; i < recs.size(); ++i) {
+      MfRec &R = recs[i];
+      std::memset(&R, 0, sizeof(R));
+      R.F = MF_.fronts[MF_.level_fronts[i]];
+      for (int c = R.F.ch_lo; c < R.F.ch_hi; ++c) {
+        const MfChild &ch = MF_.children[c];
+        const int q = c - R.F.ch_lo;
+        R.ch_ldc[q] = MF_.fronts[ch.front].u8 + MF_.kr; R.ch_coff[q] = MF_.fronts[ch.front].c_off;
+        R.ch_nown[q] = ch.n_own; R.ch_cmap[q] = ch.cmap_off; R.ch_pinv[q] = ch.pinv_off;
+      }
+    }
+    mf_.recs = dev_upload(recs);
+  }
+  mf_.dev = MfDev{mf_.recs, mf_.fronts, mf_.children, mf_.front_idx, mf_.own_rows, mf_.cmap, mf_.pinv, mf_.pe_dest, mf_.pe_ref,
                   mf_.ps_dest, mf_.pc_dest, mf_.level_fronts, mf_.ps_val, mf_.pc_val, MF_.kr, MF_.NP};
   int max_f = 0, max_b = 0;
   for (int v : MF_.smem_fwd) max_f = std::max(max_f, v);

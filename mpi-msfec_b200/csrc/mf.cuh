@@ -21,7 +21,15 @@
 namespace msfec {
 namespace {
 
+// One record per (level, position): everything a CTA needs to know about its front and its children, fetched with ONE round
+// trip (the tables level_fronts -> fronts -> children -> fronts of the plan are four dependent ones).  Built by Engine::upload_mf.
+struct MfRec {
+  MfFront F;
+  int32_t ch_ldc[8], ch_coff[8], ch_nown[8], ch_cmap[8], ch_pinv[8];   // children: column length u8 + kr, c_off, n_own, cmap_off, pinv_off
+};
+
 struct MfDev {
+  const MfRec *recs;
   const MfFront *fronts;
   const MfChild *children;
   const int *front_idx, *own_rows, *cmap, *pinv, *pe_dest, *pe_ref, *ps_dest, *pc_dest, *level_fronts;
@@ -111,7 +119,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
              const double *__restrict__ b, int NI, int k, int cell_lo, double *__restrict__ Lst, size_t l_stride,
              double *__restrict__ Cst, size_t c_stride, int *__restrict__ bad, int nbuf) {
   extern __shared__ __align__(16) double mf_smem[];
-  __shared__ int ch_coff[kMfMaxChildren], ch_ldc[kMfMaxChildren];
+  __shared__ int ch_coff[kMfMaxChildren], ch_ldc[kMfMaxChildren], ch_nown[kMfMaxChildren], ch_cmap[kMfMaxChildren], ch_pinv[kMfMaxChildren];
   __shared__ __align__(8) unsigned long long full_bar[kMfMaxStageBufs];
   constexpr int NW = NT / 32;
   constexpr int KA = S > 0 ? 2 * S : 1;          // k-steps of a full-width product
@@ -119,8 +127,8 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
                                                  // MMA work to hide the children gathers behind, so more loads are put in flight
   constexpr int TW = 4;                          // STG: row tiles of one tile column per warp (launch: row tiles <= TW * NW)
   MF_DBG_LOAD();
-  const int f = M.level_fronts[lf_off + blockIdx.x];
-  const MfFront F = M.fronts[f];
+  const MfRec *R = M.recs + lf_off + blockIdx.x;
+  const MfFront F = R->F;
   const int cell = blockIdx.y, gcell = cell_lo + cell, g = gcell / kLanes, ln = gcell % kLanes;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;
@@ -169,13 +177,13 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     double2 *P2 = reinterpret_cast<double2 *>(P);
     for (int i = tid; i < rec2; i += NT) P2[i] = make_double2(0.0, 0.0);
   }
+  if (tid < nch) {
+    ch_coff[tid] = R->ch_coff[tid]; ch_ldc[tid] = R->ch_ldc[tid]; ch_nown[tid] = R->ch_nown[tid];
+    ch_cmap[tid] = R->ch_cmap[tid]; ch_pinv[tid] = R->ch_pinv[tid];
+  }
   if (STG) {
-    if (tid < nch) {
-      const MfChild ch = M.children[F.ch_lo + tid];
-      ch_coff[tid] = M.fronts[ch.front].c_off; ch_ldc[tid] = M.fronts[ch.front].u8 + kr;
-    }
     for (int ci = 0; ci < nch; ++ci) {
-      const int po = M.children[F.ch_lo + ci].pinv_off;
+      const int po = R->ch_pinv[ci];
       for (int i = tid; i < m; i += NT) pinv_s[ci * m + i] = M.pinv[po + i];
     }
     if (tid == 0) {
@@ -264,14 +272,12 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   } else {
   // children: the leading n_own columns of a child's contribution block belong to this front's own columns
   for (int ci = 0; ci < nch; ++ci) {
-    const MfChild ch = M.children[F.ch_lo + ci];
-    const int cu8 = M.fronts[ch.front].u8, ccoff = M.fronts[ch.front].c_off;
-    const int ldc = cu8 + kr;
-    if (tid == 0) { ch_coff[ci] = ccoff; ch_ldc[ci] = ldc; }
-    const double *Cc = Cst + (size_t)cell * c_stride + ccoff;
-    const int *cmap = M.cmap + ch.cmap_off;
-    for (int i = tid; i < m; i += NT) pinv_s[ci * m + i] = M.pinv[ch.pinv_off + i];
-    for (int j = warp; j < ((dbg & 8) ? 0 : ch.n_own); j += NW) {
+    const int ldc = ch_ldc[ci];
+    const double *Cc = Cst + (size_t)cell * c_stride + ch_coff[ci];
+    const int *cmap = M.cmap + ch_cmap[ci];
+    const int po = ch_pinv[ci];
+    for (int i = tid; i < m; i += NT) pinv_s[ci * m + i] = M.pinv[po + i];
+    for (int j = warp; j < ((dbg & 8) ? 0 : ch_nown[ci]); j += NW) {
       const int cj = cmap[j];
       const double *col = Cc + (size_t)j * ldc;
       // eight independent loads in flight per lane (two columns per pass with sixteen loads measured slower: registers)
@@ -563,8 +569,7 @@ __global__ void __launch_bounds__(NT)
 k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t l_stride, double *__restrict__ xT) {
   extern __shared__ __align__(16) double mf_smem[];
   constexpr int NW = NT / 32;
-  const int f = M.level_fronts[lf_off + blockIdx.x];
-  const MfFront F = M.fronts[f];
+  const MfFront F = M.recs[lf_off + blockIdx.x].F;
   const int cell = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;
   const int s8 = F.s8, u8 = F.u8, kr = M.kr, NP = M.NP, ldx = s8 + 4, m = s8 + u8 + kr, ldt = kr + 4;
