@@ -628,13 +628,13 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
       for (; r0 < nr; r0 += 4) dmma_m8n8k4(a0[0], a1[0], A[r0 * ldx], B[r0 * ldt]);
       const double s0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
       const int c = ct * 8 + fr, j = jt * 8 + 2 * fk;
-      if (r_lo == 0) { ts[c * ldt + j] = P[(s8 + u8 + j) * ldx + c] - s0; ts[c * ldt + j + 1] = P[(s8 + u8 + j + 1) * ldx + c] - s1; }
-      else { ts[c * ldt + j] -= s0; ts[c * ldt + j + 1] -= s1; }
+      double v0 = (r_lo == 0 ? P[(s8 + u8 + j) * ldx + c] : ts[c * ldt + j]) - s0;
+      double v1 = (r_lo == 0 ? P[(s8 + u8 + j + 1) * ldx + c] : ts[c * ldt + j + 1]) - s1;
+      if (r_lo + CH >= u8) { const double di = dinv[c]; v0 *= di; v1 *= di; }   // last chunk: t = D^-1 (...)
+      ts[c * ldt + j] = v0; ts[c * ldt + j + 1] = v1;
     }
     r_lo += CH; ib ^= 1;
   } while (r_lo < u8);
-  __syncthreads();
-  for (int o = tid; o < s8 * kr; o += NT) { const int c = o / kr, j = o - c * kr; ts[c * ldt + j] *= dinv[c]; }
   __syncthreads();
   // L11^T x = t, 8 unknowns at a time, last tile first; below a pivot tile the panel holds X = L D
   for (int p = s8 / 8 - 1; p >= 0; --p) {
@@ -652,21 +652,28 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
     }
     __syncthreads();
     if (c0 > 0) {
-      // t(cp, j) -= (1 / d_cp) sum_i X(c0 + i, cp) x(c0 + i, j) for the columns before the tile: (cp, j) pairs over all threads,
-      // j fastest (kr is a multiple of 8: the 32 lanes of a warp cover 4 / 3 values of cp, x is read without bank conflicts)
-      for (int o = tid; o < c0 * kr; o += NT) {
-        const int cp = o / kr, j = o - cp * kr;
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc = fma(P[(c0 + i) * ldx + cp], ts[(c0 + i) * ldt + j], acc);
-        ts[cp * ldt + j] -= acc * dinv[cp];
+      // t(cp, j) -= (1 / d_cp) sum_i X(c0 + i, cp) x(c0 + i, j) for the columns before the tile: 8 x 8 tiles (cp-tile, j-tile) on
+      // the tensor cores, two k-steps over the eight unknowns just solved (m = cp, n = j, k = i)
+      for (int tix = warp; tix < p * JT; tix += NW) {
+        const int cpt = tix / JT, jt = tix - cpt * JT;
+        double a0 = 0.0, a1 = 0.0;
+        const double *A = P + (c0 + fk) * ldx + cpt * 8 + fr;
+        const double *B = ts + (c0 + fk) * ldt + jt * 8 + fr;
+        dmma_m8n8k4(a0, a1, A[0], B[0]);
+        dmma_m8n8k4(a0, a1, A[4 * ldx], B[4 * ldt]);
+        const int c = cpt * 8 + fr, j = jt * 8 + 2 * fk;
+        const double di = dinv[c];
+        ts[c * ldt + j] -= a0 * di; ts[c * ldt + j + 1] -= a1 * di;
       }
       __syncthreads();
     }
   }
   // own solution: s8 consecutive rows of xT, one contiguous block (columns k .. kr are zero right-hand sides: x = 0)
   double *xo = xc + (size_t)F.own_base * kr;
-  for (int o = tid; o < s8 * kr; o += NT) { const int c = o / kr, j = o - c * kr; xo[o] = ts[c * ldt + j]; }
+  for (int o = tid; o < s8 * kr2; o += NT) {
+    const int c = o / kr2, q = o - c * kr2;
+    reinterpret_cast<double2 *>(xo)[o] = *reinterpret_cast<const double2 *>(ts + c * ldt + 2 * q);
+  }
 }
 
 // xT[cell][NP][kr] (padded elimination order, per cell) -> x[g][row][k][32] (interior numbering, cell-interleaved), transposed
