@@ -99,6 +99,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 // k_mf_backward: the record, a chunk of x of the reached unknowns (<= kMfBwdChunk rows x (kr + 4)), t / x of the own
 // unknowns (s8 x (kr + 4)); the positions of the reached unknowns of two chunks sit in static shared memory
 constexpr int kMfBwdChunk = 64;
+constexpr int kMfBwdWarpSolve = 48;   // fronts up to this many own columns: barrier-free back-substitution, one warp per 8 right-hand sides
 __host__ __device__ inline size_t mf_bwd_smem_bytes(int m, int ldx, int s8, int u8, int kr) {
   const int ch = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
   return ((size_t)mf_record_doubles(m, ldx, s8) + (size_t)(ch + s8) * (kr + 4)) * sizeof(double);
@@ -637,6 +638,57 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   } while (r_lo < u8);
   __syncthreads();
   // L11^T x = t, 8 unknowns at a time, last tile first; below a pivot tile the panel holds X = L D
+  if (s8 <= kMfBwdWarpSolve) {
+    // Narrow fronts: the right-hand sides are independent, so each warp takes one tile of 8 of them through the whole
+    // back-substitution without a CTA barrier.  The unit-lower pivot tiles are inverted in place first (one warp per tile, lane =
+    // column); then per tile  x = L^-T t  and the update of the earlier tiles are 8 x 8 products on the tensor cores.
+    double *Lw = const_cast<double *>(Ld);
+    for (int pt = warp; pt < CT; pt += NW) {
+      double y[8];
+      const double *Lt = Ld + pt * 64;
+      const int c = lane & 7;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double v = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < i; ++q) v = fma(-Lt[i * 8 + q], y[q], v);   // y[q] = 0 for q < c
+        y[i] = v;
+      }
+      __syncwarp();
+      if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Lw[pt * 64 + i * 8 + c] = y[i];
+      }
+    }
+    __syncthreads();
+    for (int jt = warp; jt < JT; jt += NW) {
+      const int j = jt * 8 + 2 * fk;
+      for (int p = CT - 1; p >= 0; --p) {
+        const int c0 = p * 8;
+        const double *B = ts + (c0 + fk) * ldt + jt * 8 + fr;
+        {
+          double a0 = 0.0, a1 = 0.0;
+          const double *A = Ld + (c0 + fk) * 8 + fr;          // A[m = i][k] = Linv(k, i)
+          dmma_m8n8k4(a0, a1, A[0], B[0]);
+          dmma_m8n8k4(a0, a1, A[32], B[4 * ldt]);
+          __syncwarp();
+          ts[(c0 + fr) * ldt + j] = a0; ts[(c0 + fr) * ldt + j + 1] = a1;
+          __syncwarp();
+        }
+        for (int cpt = 0; cpt < p; ++cpt) {
+          double a0 = 0.0, a1 = 0.0;
+          const double *A = P + (c0 + fk) * ldx + cpt * 8 + fr;
+          dmma_m8n8k4(a0, a1, A[0], B[0]);
+          dmma_m8n8k4(a0, a1, A[4 * ldx], B[4 * ldt]);
+          const int c = cpt * 8 + fr;
+          const double di = dinv[c];
+          ts[c * ldt + j] -= a0 * di; ts[c * ldt + j + 1] -= a1 * di;
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  } else
   for (int p = s8 / 8 - 1; p >= 0; --p) {
     const int c0 = p * 8;
     if (tid < kr) {
