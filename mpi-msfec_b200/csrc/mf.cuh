@@ -51,7 +51,7 @@ constexpr int kMfFastChildren = 2;   // children handled by the unrolled gather 
 
 // Per-front record in the factor storage (written by k_mf_forward, read by k_mf_backward): the shared-memory image of
 // the forward kernel, copied verbatim (one flat coalesced copy each way, no index arithmetic):
-//   [ panel m x ldx | 1/d (s8) | d (s8) | unit-lower factors of the 8 x 8 pivot tiles (s8 x 8) ]
+//   [ panel m x ldx | 1/d (s8) | d (s8) | INVERSES of the unit-lower factors of the 8 x 8 pivot tiles (s8 x 8) ]
 // Panel rows below a pivot tile hold X = L D (unscaled); the consumers multiply by 1/d.
 __host__ __device__ inline int mf_record_doubles(int m, int ldx, int s8) { return m * ldx + 10 * s8; }
 
@@ -299,11 +299,13 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
   }
   }
 
-  // ---- factor: 8 columns at a time ---------------------------------------------------------------------------
+  // ---- factor: 8 columns at a time.  Row tile R of the panel belongs to warp R mod NW for the whole factorisation. ---------
   const int NS = s8 / 8, MT = m / 8;
 #pragma unroll
   for (int q = 0; q < ((dbg & 64) ? 0 : (S > 0 ? S : NS)); ++q) {
     const int c0 = q * 8;
+    const int pw = q % NW;                                   // the warp that owns the pivot tile
+    const int Rf = q + ((warp - q) % NW + NW) % NW;          // this warp's first row tile >= q
     if (q > 0) {
       // left-looking update of tile column q:  P(R, q) -= X(R, 0:c0) L(q, 0:c0)^T   (L = X D^-1), four row tiles of a
       // warp at a time (independent accumulator chains).  MMA m = column inside the tile, n = row, k = earlier columns
@@ -313,7 +315,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
 #pragma unroll
         for (int t = 0; t < KA; ++t) af[t] = t < 2 * q ? -Arow[4 * t] * dinv[4 * t + fk] : 0.0;
       }
-      for (int R0 = q + warp; R0 < MT; R0 += 4 * NW) {
+      for (int R0 = Rf; R0 < MT; R0 += 4 * NW) {
         double acc[4][2];
         double *tp[4];
         const double *Brow[4];
@@ -342,12 +344,12 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         for (int u = 0; u < 4; ++u)
           if (R0 + u * NW < MT) { tp[u][0] = acc[u][0]; tp[u][ldx] = acc[u][1]; }
       }
-      __syncthreads();
     }
-    // LDL^T of the pivot tile by warp 0: lane (i = lane & 7) = row, pivot column broadcast by shuffles; the unit-lower
-    // factor and the pivots go to shared memory (an earlier version let every thread factor the tile redundantly in
-    // registers: no barrier, but 4-8 x the FP64 work, which saturated the FP64 pipe of the small fronts)
-    if (warp == 0) {
+    // LDL^T of the pivot tile by the warp that has just updated it (the others are still updating their tiles): lane (i = lane & 7)
+    // = row, pivot column broadcast by shuffles; pivots to shared memory, then the unit-lower factor is inverted in place (lane =
+    // column, forward substitution on the unit vectors): the rows below are solved with it on the tensor cores
+    if (warp == pw) {
+      __syncwarp();
       const int i = lane & 7;
       double a[8];
 #pragma unroll
@@ -367,31 +369,50 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         if (i > p) a[p] = l;
         if (lane == p) { dval[c0 + p] = d; dinv[c0 + p] = inv; }
       }
+      double *Lt = Ld + c0 * 8;
       if (lane < 8) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Ld[(c0 + i) * 8 + j] = (j < i) ? a[j] : 0.0;
+        for (int j = 0; j < 8; ++j) Lt[i * 8 + j] = (j < i) ? a[j] : 0.0;
       }
       if (!ok && lane == 0) atomicExch(bad, 1);
+      __syncwarp();
+      double y[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        double v = (r == i) ? 1.0 : 0.0;                     // column i of L^-1
+#pragma unroll
+        for (int t = 0; t < r; ++t) v = fma(-Lt[r * 8 + t], y[t], v);
+        y[r] = v;
+      }
+      __syncwarp();
+      if (lane < 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) Lt[r * 8 + i] = y[r];
+      }
     }
     __syncthreads();
-    // rows below the pivot tile: X = A L^-T, one thread per row, L broadcast from shared memory
-    for (int r = c0 + 8 + tid; r < m; r += NT) {
-      double *row = P + r * ldx + c0;
-      const double *Lt = Ld + c0 * 8;
-      double x[8];
+    // rows below the pivot tile: X = A L^-T on the tensor cores (m = column, n = row, k = column of A), in place: a warp
+    // reads the 8 x 8 tile it owns as B fragments and writes it back as accumulators
+    {
+      const double l0 = Ld[(c0 + fr) * 8 + fk], l1 = Ld[(c0 + fr) * 8 + 4 + fk];
+      for (int R0 = (Rf > q ? Rf : Rf + NW); R0 < MT; R0 += 4 * NW) {
+        double acc[4][2];
+        double *tp[4];
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) { const double2 v = *reinterpret_cast<const double2 *>(row + j); x[j] = v.x; x[j + 1] = v.y; }
-#pragma unroll
-      for (int j = 1; j < 8; ++j) {
-#pragma unroll
-        for (int t = 0; t < j; t += 2) {
-          const double2 lv = *reinterpret_cast<const double2 *>(Lt + j * 8 + t);
-          x[j] = fma(-x[t], lv.x, x[j]);
-          if (t + 1 < j) x[j] = fma(-x[t + 1], lv.y, x[j]);
+        for (int u = 0; u < 4; ++u) {
+          const int R = min(R0 + u * NW, MT - 1);
+          const double *Br = P + (R * 8 + fr) * ldx + c0 + fk;
+          tp[u] = P + (R * 8 + 2 * fk) * ldx + c0 + fr;
+          acc[u][0] = acc[u][1] = 0.0;
+          const double b0 = Br[0], b1 = Br[4];
+          dmma_m8n8k4(acc[u][0], acc[u][1], l0, b0);
+          dmma_m8n8k4(acc[u][0], acc[u][1], l1, b1);
         }
-      }
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) *reinterpret_cast<double2 *>(row + j) = make_double2(x[j], x[j + 1]);
+        for (int u = 0; u < 4; ++u)
+          if (R0 + u * NW < MT) { tp[u][0] = acc[u][0]; tp[u][ldx] = acc[u][1]; }
+      }
     }
     __syncthreads();
   }
@@ -576,7 +597,7 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
   const int s8 = F.s8, u8 = F.u8, kr = M.kr, NP = M.NP, ldx = s8 + 4, m = s8 + u8 + kr, ldt = kr + 4;
   double *P = mf_smem;                          // [m][ldx]
   const double *dinv = P + m * ldx;             // [s8]
-  const double *Ld = dinv + 2 * s8;             // [s8][8]
+  const double *Ld = dinv + 2 * s8;             // [s8][8]   inverses of the unit-lower pivot tiles
   const int rec = mf_record_doubles(m, ldx, s8);
   const int CH = u8 < kMfBwdChunk ? u8 : kMfBwdChunk;
   double *xu = P + rec;                         // [CH][ldt]  x of the reached unknowns, one chunk of rows at a time
@@ -637,30 +658,11 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
     r_lo += CH; ib ^= 1;
   } while (r_lo < u8);
   __syncthreads();
-  // L11^T x = t, 8 unknowns at a time, last tile first; below a pivot tile the panel holds X = L D
+  // L11^T x = t, 8 unknowns at a time, last tile first; below a pivot tile the panel holds X = L D, the record carries the
+  // inverses of the unit-lower pivot tiles:  x = Linv^T t  and the update of the earlier tiles are 8 x 8 products on the tensor cores
   if (s8 <= kMfBwdWarpSolve) {
-    // Narrow fronts: the right-hand sides are independent, so each warp takes one tile of 8 of them through the whole
-    // back-substitution without a CTA barrier.  The unit-lower pivot tiles are inverted in place first (one warp per tile, lane =
-    // column); then per tile  x = L^-T t  and the update of the earlier tiles are 8 x 8 products on the tensor cores.
-    double *Lw = const_cast<double *>(Ld);
-    for (int pt = warp; pt < CT; pt += NW) {
-      double y[8];
-      const double *Lt = Ld + pt * 64;
-      const int c = lane & 7;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        double v = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int q = 0; q < i; ++q) v = fma(-Lt[i * 8 + q], y[q], v);   // y[q] = 0 for q < c
-        y[i] = v;
-      }
-      __syncwarp();
-      if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) Lw[pt * 64 + i * 8 + c] = y[i];
-      }
-    }
-    __syncthreads();
+    // narrow fronts: the right-hand sides are independent, so each warp takes one tile of 8 of them through the whole
+    // back-substitution without a CTA barrier
     for (int jt = warp; jt < JT; jt += NW) {
       const int j = jt * 8 + 2 * fk;
       for (int p = CT - 1; p >= 0; --p) {
@@ -690,22 +692,19 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
     __syncthreads();
   } else
   for (int p = s8 / 8 - 1; p >= 0; --p) {
+    // wide fronts: the tiles of the update go to all warps, two barriers per pivot tile
     const int c0 = p * 8;
-    if (tid < kr) {
-      double x[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = ts[(c0 + i) * ldt + tid];
-#pragma unroll
-      for (int i = 6; i >= 0; --i)
-#pragma unroll
-        for (int i2 = i + 1; i2 < 8; ++i2) x[i] = fma(-Ld[(c0 + i2) * 8 + i], x[i2], x[i]);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) ts[(c0 + i) * ldt + tid] = x[i];
+    for (int jt = warp; jt < JT; jt += NW) {
+      double a0 = 0.0, a1 = 0.0;
+      const double *A = Ld + (c0 + fk) * 8 + fr;
+      const double *B = ts + (c0 + fk) * ldt + jt * 8 + fr;
+      dmma_m8n8k4(a0, a1, A[0], B[0]);
+      dmma_m8n8k4(a0, a1, A[32], B[4 * ldt]);
+      __syncwarp();
+      ts[(c0 + fr) * ldt + jt * 8 + 2 * fk] = a0; ts[(c0 + fr) * ldt + jt * 8 + 2 * fk + 1] = a1;
     }
     __syncthreads();
     if (c0 > 0) {
-      // t(cp, j) -= (1 / d_cp) sum_i X(c0 + i, cp) x(c0 + i, j) for the columns before the tile: 8 x 8 tiles (cp-tile, j-tile) on
-      // the tensor cores, two k-steps over the eight unknowns just solved (m = cp, n = j, k = i)
       for (int tix = warp; tix < p * JT; tix += NW) {
         const int cpt = tix / JT, jt = tix - cpt * JT;
         double a0 = 0.0, a1 = 0.0;

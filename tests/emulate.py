@@ -234,7 +234,12 @@ def emulate_multifrontal(bb, vals, kscale, b):
             Pn[r, (r // 8) * 8:(r // 8) * 8 + 8] = np.nan        # pivot tile: garbage in the kernel, never read
         rec[m * ldx:m * ldx + s8] = 1.0 / d
         rec[m * ldx + s8:m * ldx + 2 * s8] = d
-        rec[m * ldx + 2 * s8:] = Ld.reshape(-1)
+        # the record keeps the INVERSES of the unit-lower pivot tiles (the rows below are solved with them on the tensor cores,
+        # and so is the back-substitution)
+        Li = np.zeros((s8, 8))
+        for q in range(s8 // 8):
+            Li[q * 8:q * 8 + 8] = np.linalg.inv(np.eye(8) + Ld[q * 8:q * 8 + 8])
+        rec[m * ldx + 2 * s8:] = Li.reshape(-1)
         Lst[F["l_off"]:F["l_off"] + len(rec)] = rec
         dall[F["own_base"]:F["own_base"] + s8] = d
         # contribution block
@@ -270,18 +275,19 @@ def emulate_multifrontal(bb, vals, kscale, b):
         rec = Lst[F["l_off"]:F["l_off"] + m * ldx + 10 * s8]
         Pn = rec[:m * ldx].reshape(m, ldx)
         dinv = rec[m * ldx:m * ldx + s8]
-        Ld = rec[m * ldx + 2 * s8:].reshape(s8, 8)
+        Li = rec[m * ldx + 2 * s8:].reshape(s8, 8)
         idx = T["front_idx"][F["idx_off"]:F["idx_off"] + s8 + u8]
         xu = np.zeros((u8, kr))
         for r in range(u8):
             if idx[s8 + r] >= 0:
                 xu[r] = xp[idx[s8 + r]]
         t = (Pn[s8 + u8:, :s8].T - Pn[s8:s8 + u8, :s8].T @ xu) * dinv[:, None]
-        L11 = np.eye(s8)
-        for r in range(s8):
-            for c in range(r):
-                L11[r, c] = Ld[r, c % 8] if r // 8 == c // 8 else Pn[r, c] * dinv[c]
-        xo = np.linalg.solve(L11.T, t)
+        # L11^T x = t tile by tile, last tile first: x_p = Linv_p^T t_p, then t_c -= (1 / d_c) X(p rows, c)^T x_p for c before p
+        xo = t.copy()
+        for q in range(s8 // 8 - 1, -1, -1):
+            c0 = q * 8
+            xo[c0:c0 + 8] = Li[c0:c0 + 8].T @ xo[c0:c0 + 8]
+            xo[:c0] -= (Pn[c0:c0 + 8, :c0].T @ xo[c0:c0 + 8]) * dinv[:c0, None]
         xp[F["own_base"]:F["own_base"] + s8] = xo
     inv = T["inv_perm"]
     x = np.zeros_like(b)
