@@ -728,25 +728,35 @@ k_mf_backward(MfDev M, int lf_off, int k, const double *__restrict__ Lst, size_t
 }
 
 // xT[cell][NP][kr] (padded elimination order, per cell) -> x[g][row][k][32] (interior numbering, cell-interleaved), transposed
-// through shared memory so that both sides are coalesced.  cell_lo is a multiple of 32.
-// grid (NP / 4, ceil(cells / 32)), block (32, 8)
+// through shared memory so that both sides move whole sectors.  cell_lo is a multiple of 32, NP of 8, kr even.
+// grid (NP / 4, ceil(cells / 32)), block (32, 8): two threads read the k values of one (cell, position) as 16-byte pairs,
+// then warp w writes the rows (position, rhs j = w, w + 8, ...) with the 32 cells of the group side by side.
 __global__ void __launch_bounds__(256)
 k_mf_scatter_x(int NP, int NI, int k, int kr, const int *__restrict__ inv_perm, const double *__restrict__ xT, int cell_lo,
                int n_cells, double *__restrict__ x) {
-  constexpr int PC = 4;                                    // positions per block
-  __shared__ double tile[kLanes][PC * 24 + 1];
-  const int lane = threadIdx.x, w = threadIdx.y;
+  constexpr int PC = 4;                                    // positions per block (21 KB of shared memory: 10 CTAs per SM)
+  __shared__ double tile[kLanes][PC * kMaxK + 1];          // [cell][position][rhs < k]
+  __shared__ int rows[PC];
+  const int lane = threadIdx.x, w = threadIdx.y, t = w * 32 + lane;
   const int p0 = blockIdx.x * PC, c0 = blockIdx.y * kLanes;
-  const int g = (cell_lo + c0) / kLanes, W = PC * kr;
-  for (int c = w; c < kLanes; c += 8) {
-    const double *src = xT + ((size_t)(c0 + c) * NP + p0) * kr;
-    for (int o = lane; o < W; o += 32) tile[c][o] = (c0 + c < n_cells) ? src[o] : 0.0;
+  const int g = (cell_lo + c0) / kLanes;
+  if (t < PC) rows[t] = inv_perm[p0 + t];
+  {
+    const int half = t >> 7, c = (t & 127) >> 2, pp = t & 3;
+    const bool ok = c0 + c < n_cells;
+    const double2 *src = reinterpret_cast<const double2 *>(xT + ((size_t)(c0 + c) * NP + p0 + pp) * kr);
+    double *dst = &tile[c][pp * k];
+    for (int q = half; 2 * q < k; q += 2) {
+      const double2 v = ok ? src[q] : make_double2(0.0, 0.0);
+      dst[2 * q] = v.x;
+      if (2 * q + 1 < k) dst[2 * q + 1] = v.y;
+    }
   }
   __syncthreads();
-  for (int o = w; o < PC * k; o += 8) {
-    const int pp = o / k, j = o - pp * k;
-    const int row = inv_perm[p0 + pp];
-    if (row >= 0) x[(((size_t)g * NI + row) * k + j) * kLanes + lane] = tile[lane][pp * kr + j];
+  for (int pp = 0; pp < PC; ++pp) {
+    const int row = rows[pp];
+    if (row < 0) continue;
+    for (int j = w; j < k; j += 8) x[(((size_t)g * NI + row) * k + j) * kLanes + lane] = tile[lane][pp * k + j];
   }
 }
 
