@@ -569,6 +569,13 @@ __global__ void k_apply_full(OpDev A, int NF, int N0, int k0, int kg, int n_slot
 // transposing stores are 2-way conflicted at worst) and each of its 8 warps runs the 24x24 (3x3 m8n8k4 tiles)
 // product of 4 cells.  Slices are summed by k_gram_reduce, so the result is deterministic.
 // grid (groups, n_slices), block 256
+// cp.async (LDGSTS) helpers of this kernel (the factorisation kernels have their own further down)
+__device__ __forceinline__ void gram_cp8(void *smem, const void *gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void gram_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void gram_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 constexpr int kGramDT = 8;                     // fine DoFs per staged tile
 constexpr int kGramJ = 24;                     // k padded to 3 MMA tiles
 constexpr int kGramCS = kGramDT * kGramJ + 1;  // per-cell stride in shared memory (odd)
@@ -579,7 +586,10 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
             const double *__restrict__ grhs, int rhs_off, int n_rhs, int n_slices,
             double *__restrict__ Mpart, double *__restrict__ rpart) {
   extern __shared__ double gram_smem[];
-  double *Zs = gram_smem, *Ys = gram_smem + kLanes * kGramCS;
+  // two stage buffers of [Z tile | Y tile]: the tile of the next 8 fine DoFs arrives by cp.async (8 bytes per copy, transposed on
+  // the way: consecutive threads read consecutive cells, 256-byte coalesced, and write per-cell panels) while the tensor cores work
+  // on the current one
+  constexpr int kStage = 2 * kLanes * kGramCS;
   const int g = blockIdx.x, slice = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int fr = lane >> 2, fk = lane & 3;
   const int per = ((NF + n_slices - 1) / n_slices + kGramDT - 1) / kGramDT * kGramDT;
@@ -595,18 +605,26 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
 #pragma unroll
       for (int b = 0; b < 3; ++b) acc[c][a][b][0] = acc[c][a][b][1] = 0.0;
   double racc = 0.0;                                       // rhs: thread (cell = lane, i = warp + 8*q) handled below
-  for (int idx = tid; idx < kLanes * kGramCS; idx += NT) { Zs[idx] = 0.0; Ys[idx] = 0.0; }   // zero the j padding once
+  for (int idx = tid; idx < 2 * kStage; idx += NT) gram_smem[idx] = 0.0;   // zero the j padding (and the tail rows) once
   __syncthreads();
-  for (int d0 = d_lo; d0 < d_hi; d0 += kGramDT) {
-    // stage: element (dd, j, cell) ; consecutive threads -> consecutive cells (coalesced 256 B global reads)
+  auto stage = [&](int d0, int buf) {
+    double *Zs = gram_smem + buf * kStage, *Ys = Zs + kLanes * kGramCS;
     for (int idx = tid; idx < kGramDT * kg * kLanes; idx += NT) {
       const int cell = idx & 31, t = idx >> 5, j = t % kg, dd = t / kg;
-      const bool ok = d0 + dd < d_hi;
       const size_t o = ((size_t)(d0 + dd) * kg + j) * kLanes + cell;
-      Zs[cell * kGramCS + dd * kGramJ + j] = ok ? z[o] : 0.0;
-      Ys[cell * kGramCS + dd * kGramJ + j] = ok ? y[o] : 0.0;
+      const int so = cell * kGramCS + dd * kGramJ + j;
+      if (d0 + dd < d_hi) { gram_cp8(Zs + so, z + o); gram_cp8(Ys + so, y + o); }
+      else { Zs[so] = 0.0; Ys[so] = 0.0; }
     }
+    gram_cp_commit();
+  };
+  int buf = 0;
+  if (d_lo < d_hi) stage(d_lo, 0);
+  for (int d0 = d_lo; d0 < d_hi; d0 += kGramDT) {
+    if (d0 + kGramDT < d_hi) { stage(d0 + kGramDT, buf ^ 1); gram_cp_wait<1>(); }
+    else gram_cp_wait<0>();
     __syncthreads();
+    const double *Zs = gram_smem + buf * kStage, *Ys = Zs + kLanes * kGramCS;
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
       const double *zc = Zs + (warp + kGramWarps * c) * kGramCS, *yc = Ys + (warp + kGramWarps * c) * kGramCS;
@@ -624,7 +642,8 @@ k_gram_dmma(int NF, int kg, const double *__restrict__ Z, int gz0, const double 
           for (int b = 0; b < 3; ++b) dmma_m8n8k4(acc[c][a][b][0], acc[c][a][b][1], af[a], bf[b]);
       }
     }
-    __syncthreads();
+    __syncthreads();                                       // the buffer may be overwritten by the stage after next
+    buf ^= 1;
   }
   // partial M: Mpart[slice][cell in batch][24][24]
 #pragma unroll
@@ -806,7 +825,7 @@ class Engine {
     CUDA_OK(cudaMalloc(&d_flag_, 4 * sizeof(int)));
     CUDA_OK(cudaMallocHost(&h_flag_, 4 * sizeof(int)));
     n_slots_ = T_.n_slots0 + T_.n_slots1;
-    CUDA_OK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * kLanes * kGramCS * sizeof(double))));
+    CUDA_OK(cudaFuncSetAttribute(k_gram_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(4 * kLanes * kGramCS * sizeof(double))));
     select_solver();
     if (use_mf_) upload_mf();
     if (use_direct_) {
@@ -1674,7 +1693,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
         gram_part_size_ = need;
       }
       double *Mpart = d_gram_part_, *rpart = d_gram_part_ + (size_t)n_slices * groups * kLanes * kGramJ * kGramJ;
-      k_gram_dmma<<<dim3(groups, n_slices), 32 * kGramWarps, 2 * kLanes * kGramCS * sizeof(double), stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
+      k_gram_dmma<<<dim3(groups, n_slices), 32 * kGramWarps, 4 * kLanes * kGramCS * sizeof(double), stream_>>>(T_.NF, kg, d_Z_, gz0, d_Y_, d_grhs_, rhs_off, T_.asm_rhs.n_slots,
                                                             n_slices, Mpart, rpart);
       k_gram_reduce<<<nb, 128, 0, stream_>>>(kg, groups, n_slices, cell0, n_cells, Mpart, rpart, d_M_, d_r_);
       ++launches_;
