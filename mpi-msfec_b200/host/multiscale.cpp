@@ -334,6 +334,33 @@ template class Multiscale<MSFEC_NED_RT>;
 template class Multiscale<MSFEC_RT_DQ>;
 
 // Mirrors source/main_ned_rt.cxx:15-117: parse "-p <prm>", construct XMultiscale, run(), catch-all.
+// `set compute solution = true` inside `subsection Standard method parameters` (any nesting below it)
+static bool std_solution_requested(const std::string &prm_file) {
+  std::ifstream in(prm_file);
+  std::string line;
+  int depth = 0, std_depth = -1;
+  auto trim = [](std::string t) {
+    const size_t h = t.find('#');
+    if (h != std::string::npos) t.erase(h);
+    const size_t a = t.find_first_not_of(" \t\r"), b = t.find_last_not_of(" \t\r");
+    return a == std::string::npos ? std::string() : t.substr(a, b - a + 1);
+  };
+  while (std::getline(in, line)) {
+    const std::string t = trim(line);
+    if (t.rfind("subsection", 0) == 0) {
+      if (std_depth < 0 && t.find("Standard method parameters") != std::string::npos) std_depth = depth;
+      ++depth;
+    } else if (t == "end") {
+      --depth;
+      if (depth == std_depth) std_depth = -1;
+    } else if (std_depth >= 0 && t.rfind("set", 0) == 0 && t.find("compute solution") != std::string::npos) {
+      const size_t eq = t.find('=');
+      if (eq != std::string::npos && trim(t.substr(eq + 1)) == "true") return true;
+    }
+  }
+  return false;
+}
+
 int driver_main(int argc, char **argv, int pairing, const char *name) {
   try {
     std::string prm_file;
@@ -349,6 +376,11 @@ int driver_main(int argc, char **argv, int pairing, const char *name) {
     const int world = env_int("OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "WORLD_SIZE", 1);
     const int device = env_int("OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "LOCAL_RANK", 0);
     ParametersMs prm(prm_file, pairing);
+    // The reference's main_*.cxx first runs the fine-grid comparator (*Std, `Standard method parameters`) and then the multiscale
+    // method.  The comparator is not part of this build: say so instead of silently skipping it.
+    if (rank == 0 && std_solution_requested(prm_file))
+      std::cout << "Note: `Standard method parameters / compute solution = true`: the fine-grid comparator (" << name
+                << "Std of the reference) is not part of this build and is skipped; running the multiscale method." << std::endl;
     switch (pairing) {
       case MSFEC_Q: { Multiscale<MSFEC_Q> ms(prm, prm_file, rank, world, device, name); ms.run(); break; }
       case MSFEC_Q_NED: { Multiscale<MSFEC_Q_NED> ms(prm, prm_file, rank, world, device, name); ms.run(); break; }

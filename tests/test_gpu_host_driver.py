@@ -78,6 +78,9 @@ def test_driver_end_to_end_single_rank(msfec, host_built, tmp_path, pairing):
     prm, fname = _small_prm(tmp_path, pairing, verbose_basis=True)
     out = _run_driver(host_built, pairing, prm, {"MSFEC_NCCL": "1"})
     assert "NCCL communicator over 1 rank(s)" in out and "Outer solver completed." in out
+    # the shipped .prm files ask for the fine-grid comparator too (`Standard method parameters / compute solution = true`): it is out
+    # of scope here and the driver says so
+    assert "fine-grid comparator" in out and "is skipped" in out
     assert len(re.findall(r"Solving for basis in cell   0_2:\d\d   \[machine: .* \| rank: 0\]   \.\.\.\.\.done in", out)) == 64
     d = tmp_path / "out"
     name = EXE[pairing][6:]
