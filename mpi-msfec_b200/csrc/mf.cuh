@@ -171,7 +171,8 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
       if (has[T * nch + ci]) { issue_stage(T, ci, buf); return; }
     }
   };
-  int n_stage = 0;                              // stages consumed so far (all threads agree)
+  int s_buf = 0;                                // ring position and phase parity of the next stage to consume (all threads agree)
+  uint32_t s_par = 0;
 
   // ---- assemble the panel --------------------------------------------------------------------------------
   {
@@ -257,8 +258,8 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
     for (int q = 0; q < s8 / 8; ++q)
       for (int ci = 0; ci < nch; ++ci) {
         if (!has[q * nch + ci]) continue;
-        const int buf = n_stage % nbuf;
-        mbar_wait(&full_bar[buf], (n_stage / nbuf) & 1);
+        const int buf = s_buf;
+        mbar_wait(&full_bar[buf], s_par);
         const int *pv = pinv_s + ci * m;
         const double *sb = stg + (size_t)buf * 8 * ldcm;
         for (int o = q * 64 + tid; o < m * 8; o += NT) {
@@ -268,7 +269,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         }
         __syncthreads();                         // the buffer is free again (and the panel complete for the next child)
         if (tid < 8) issue_next(buf);
-        ++n_stage;
+        if (++s_buf == nbuf) { s_buf = 0; s_par ^= 1u; }
       }
   } else {
   // children: the leading n_own columns of a child's contribution block belong to this front's own columns
@@ -447,8 +448,8 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
       for (int u = 0; u < TW; ++u) acc[u][0] = acc[u][1] = 0.0;
       for (int ci = 0; ci < nch; ++ci) {
         if (!has[(s8 / 8 + J) * nch + ci]) continue;
-        const int buf = n_stage % nbuf;
-        mbar_wait(&full_bar[buf], (n_stage / nbuf) & 1);
+        const int buf = s_buf;
+        mbar_wait(&full_bar[buf], s_par);
         const int *pv = pinv_s + ci * m;
         const int jc = pv[colp];
         if (jc >= 0) {
@@ -465,7 +466,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         }
         __syncthreads();
         if (tid < 8) issue_next(buf);
-        ++n_stage;
+        if (++s_buf == nbuf) { s_buf = 0; s_par ^= 1u; }
       }
       if (J + warp >= RT) continue;
       const double *Arow = P + colp * ldx + fk;
