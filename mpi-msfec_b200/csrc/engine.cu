@@ -1276,7 +1276,7 @@ void Engine::upload_mf() {
     }
     if (std::getenv("MSFEC_MF_GENERIC") == nullptr && w > 0 && w / 8 <= 6) mf_level_S_[l] = w / 8;
   }
-  for (int v : MF_.smem_fwd_st) max_f = std::max(max_f, std::min(v, 231424));
+  for (int v : MF_.smem_fwd_st) if (v > 0) max_f = 231424;   // streamed variant: the ring depth (MSFEC_MF_NBUF) is chosen at launch, allow the opt-in maximum
 #define MF_SET_ATTR(NT, MINB, S)                                                                                                   \
   CUDA_OK(cudaFuncSetAttribute(k_mf_forward<NT, MINB, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));             \
   CUDA_OK(cudaFuncSetAttribute(k_mf_forward<NT, MINB, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_f));
