@@ -228,6 +228,18 @@ def test_reference_prm_configs_full_size(msfec, pairing):
     assert worst < TOL
 
 
+@pytest.mark.parametrize("solver", ["auto", "mf", "minres"])
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_one_local_refinement(msfec, pairing, solver):
+    """Smallest local problems (n = 2: one 2 x 2 x 2 box, the multifrontal tree is a single root front without reached
+    unknowns), ragged batch of 40 cells, rough random field."""
+    cells = mo.morton_cells(2)[:40]
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, 1, random_seed=7, solver=msfec.SOLVER[solver]), device=0).run(cells, np.arange(40))
+    worst = _check_cells(bb, oracle_problem(pairing, 1, random_seed=7), cells, np.arange(40), (0, 33, 39))
+    assert worst < TOL and bb.stats["residual_max"] < 1e-10
+    assert bb.stats["solver"] == (0 if solver == "minres" else 2)
+
+
 @pytest.mark.parametrize("pairing", ["Q", "RT_DQ", "Q_NED", "NED_RT"])
 def test_minres_full_size(msfec, pairing):
     """The batched MINRES path (msfec_problem.solver = MSFEC_SOLVER_MINRES; the memory fallback of the automatic selection)
