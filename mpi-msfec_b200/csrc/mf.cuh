@@ -7,12 +7,17 @@
 //                  cell-independent coupling entries, padding pivots) + rhs rows + the leading columns of the
 //                  children's contribution blocks (extend-add through `cmap`);
 //                  LDL^T of the own block / X = A L^-T of the rows below in 8-column steps: the left-looking update
-//                  runs on mma.sync.m8n8k4.f64, the 8 x 8 pivot tile is factored by one warp (lane = row, shuffles),
-//                  the rows below are solved one thread per row;
+//                  runs on mma.sync.m8n8k4.f64, the 8 x 8 pivot tile is factored by the warp that owns it (lane = row,
+//                  shuffles) and its unit-lower factor inverted in place, the rows below are solved with the inverse on
+//                  the tensor cores too;
 //                  factor record -> global (read again by k_mf_backward only);
 //                  contribution block C = sum_children C_child - X L21^T, 8 x 8 tiles on the FP64 tensor cores,
-//                  children gathered through `pinv` straight into the accumulators, 16-byte stores.
-//   k_mf_backward  x_own = L11^-T (z_own - L21^T x_reached), top-down; the product on the FP64 tensor cores.
+//                  children gathered through `pinv` straight into the accumulators -- or, where several fronts share
+//                  an SM, streamed through a shared-memory ring by cp.async.bulk + mbarrier (template flag STG) --
+//                  16-byte stores.
+//   k_mf_backward  x_own = L11^-T (z_own - L21^T x_reached), top-down; positions, record and solution rows arrive as
+//                  cp.async groups, product and back-substitution run on the FP64 tensor cores.
+//   k_mf_scatter_x padded per-cell solution -> cell-interleaved layout.
 // Everything else of a front lives in shared memory, so HBM sees: slot values and rhs once, every factor record
 // written once and read once, every contribution block written once and read once (MfPlan::bytes_fwd / _bwd).
 // Included by engine.cu.
