@@ -1384,7 +1384,7 @@ void Engine::solve_mf_batch(int groups, int nb, double kscale) {
     for (int l = MF_.n_levels - 1; l >= 0; --l) {
       const int nfl = MF_.level_off[l + 1] - MF_.level_off[l];
       // as in the forward pass: the fewer fronts fit an SM, the more warps each gets
-      if (MF_.smem_bwd[l] <= 56 * 1024)
+      if (MF_.smem_bwd[l] <= 40 * 1024)   // (the leaf fronts, 48 KB, measured 1 % faster with 8 warps)
         k_mf_backward<128><<<dim3(nfl, nc), 128, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
       else if (MF_.smem_bwd[l] <= 112 * 1024)
         k_mf_backward<256><<<dim3(nfl, nc), 256, (size_t)MF_.smem_bwd[l], stream_>>>(mf_.dev, MF_.level_off[l], k, d_mf_L_, (size_t)MF_.l_doubles, d_mf_xT_);
