@@ -117,3 +117,22 @@ def test_streamed_children_match_gathered_children(msfec, monkeypatch):
         assert rel_err(out[mode][11], Mo) < 1e-9
         bb.close()
     assert rel_err(out["1"], out["0"]) < 1e-12 and rel_err(out["2"], out["0"]) < 1e-12
+
+
+def test_multifrontal_sub_batches(msfec, monkeypatch):
+    """The multifrontal solver works through a resident batch in sub-batches sized by its storage budget (factor records,
+    contribution arena, padded solution are re-used from one sub-batch to the next).  Forcing 64-cell sub-batches on a ragged
+    200-cell build must not change a single bit of the element matrices."""
+    cells = np.concatenate([mo.morton_cells(2), mo.morton_cells(2), mo.morton_cells(2), mo.morton_cells(2)[:8]])
+    ids = np.arange(len(cells)) % 64
+    out = []
+    for sub in (None, "64"):
+        if sub:
+            monkeypatch.setenv("MSFEC_MF_BATCH", sub)
+        bb = msfec.BasisBuilder(lib_problem(msfec, "NED_RT", 3, random_seed=3, solver=msfec.SOLVER["mf"]), device=0).run(cells, ids)
+        assert bb.stats["residual_max"] < 1e-10 and bb.stats["not_converged"] == 0
+        out.append((bb.get_global_element_matrix().copy(), bb.get_global_element_rhs().copy(), bb.stats["mf_launches"]))
+        bb.close()
+    assert out[1][2] == 4 * out[0][2]                      # 4 sub-batches instead of 1
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[0][0][:64], out[0][0][64:128])   # the same cells again give the same bits
