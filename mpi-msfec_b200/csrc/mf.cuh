@@ -327,7 +327,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         const double *Brow[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int R = min(R0 + u * NW, MT - 1);
+          const int R = R0 + u * NW < MT ? R0 + u * NW : R0;   // past the end: the warp's own first tile again (result discarded)
           tp[u] = P + (R * 8 + 2 * fk) * ldx + c0 + fr;
           Brow[u] = P + (R * 8 + fr) * ldx + fk;
           acc[u][0] = tp[u][0]; acc[u][1] = tp[u][ldx];
@@ -406,7 +406,7 @@ k_mf_forward(MfDev M, int lf_off, const double *__restrict__ vals, int n_slots, 
         double *tp[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int R = min(R0 + u * NW, MT - 1);
+          const int R = R0 + u * NW < MT ? R0 + u * NW : R0;   // past the end: the warp's own first tile again (result discarded)
           const double *Br = P + (R * 8 + fr) * ldx + c0 + fk;
           tp[u] = P + (R * 8 + 2 * fk) * ldx + c0 + fr;
           acc[u][0] = acc[u][1] = 0.0;
