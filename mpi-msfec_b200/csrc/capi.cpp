@@ -249,12 +249,15 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
   } catch (const std::bad_alloc &) {
     delete ctx;
     return set_error(nullptr, MSFEC_ENOMEM, "out of memory");
+  } catch (const NoDeviceError &e) {
+    delete ctx;
+    return set_error(nullptr, MSFEC_ENODEVICE, e.what());
+  } catch (const ParseError &e) {
+    delete ctx;
+    return set_error(nullptr, MSFEC_EPARSE, e.what());
   } catch (const std::exception &e) {
     delete ctx;
-    const std::string msg = e.what();
-    const bool nodev = msg.find("no CUDA device") != std::string::npos || msg.find("not sm_100") != std::string::npos;
-    const bool parse = msg.find("expression") != std::string::npos || msg.find("constant") != std::string::npos;
-    return set_error(nullptr, nodev ? MSFEC_ENODEVICE : (parse ? MSFEC_EPARSE : MSFEC_ECUDA), msg);
+    return set_error(nullptr, MSFEC_ECUDA, e.what());
   }
 }
 

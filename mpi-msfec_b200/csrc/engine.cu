@@ -807,12 +807,12 @@ class Engine {
       : spec_(spec), T_(topo), P_(plan), MF_(mf), device_(device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
-    if (e != cudaSuccess || count == 0) throw std::runtime_error("no CUDA device available (there is no CPU fallback)");
-    if (device >= count) throw std::runtime_error("CUDA device index out of range");
+    if (e != cudaSuccess || count == 0) throw NoDeviceError("no CUDA device available (there is no CPU fallback)");
+    if (device >= count) throw NoDeviceError("CUDA device index out of range");
     CUDA_OK(cudaSetDevice(device));
     cudaDeviceProp prop{};
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) throw std::runtime_error(std::string("device '") + prop.name + "' is not sm_100 class");
+    if (prop.major < 10) throw NoDeviceError(std::string("device '") + prop.name + "' is not sm_100 class");
     CUDA_OK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
     for (auto &ev : ev_) CUDA_OK(cudaEventCreate(&ev));
     for (auto &ev : ev_sp_) CUDA_OK(cudaEventCreate(&ev));

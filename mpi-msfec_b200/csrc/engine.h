@@ -1,5 +1,6 @@
 // Device engine of the basis build (declarations shared by engine.cu and capi.cpp).
 #pragma once
+#include <stdexcept>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -37,7 +38,12 @@ struct ProblemSpec {          // owned copy of msfec_problem with strings resolv
 
 class Engine;   // defined in engine.cu
 
-// Factory; throws std::runtime_error.  device >= 0.
+// no usable sm_100 device (-> MSFEC_ENODEVICE at the C ABI; there is no CPU fallback)
+struct NoDeviceError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+// Factory; throws NoDeviceError, std::invalid_argument, std::runtime_error (CUDA).  device >= 0.
 Engine *engine_create(int device, const ProblemSpec &spec, const Topology &topo, const DirectPlan &plan, const MfPlan &mf);
 void engine_destroy(Engine *e);
 int engine_build(Engine *e, int n_cells, const double *corners, const int64_t *cell_ids, double *elem_matrix,

@@ -20,7 +20,7 @@ struct Parser {
   Parser(const std::string &s_, const std::map<std::string, double> &c) : s(s_), constants(c) {}
 
   [[noreturn]] void fail(const std::string &why) const {
-    throw std::runtime_error("expression '" + s + "': " + why + " at offset " + std::to_string(pos));
+    throw ParseError("expression '" + s + "': " + why + " at offset " + std::to_string(pos));
   }
   void skip() { while (pos < s.size() && std::isspace((unsigned char)s[pos])) ++pos; }
   bool sym(char c) {
@@ -141,7 +141,7 @@ std::map<std::string, double> expr_parse_constants(const std::string &s) {
     const std::string item = trim(s.substr(b, e - b));
     if (!item.empty()) {
       const size_t eq = item.find('=');
-      if (eq == std::string::npos) throw std::runtime_error("bad constant '" + item + "'");
+      if (eq == std::string::npos) throw ParseError("bad constant '" + item + "'");
       out[trim(item.substr(0, eq))] = std::strtod(item.c_str() + eq + 1, nullptr);
     }
     b = e + 1;

@@ -7,6 +7,7 @@
 // coefficient-sampling kernel interpret.
 #pragma once
 #include <cmath>
+#include <stdexcept>
 #include <string>
 #include <map>
 #include <vector>
@@ -18,6 +19,11 @@
 #endif
 
 namespace msfec {
+
+// malformed expression / constants string of a .prm (-> MSFEC_EPARSE at the C ABI)
+struct ParseError : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
 
 enum ExprOp : int {
   OP_CONST = 0, OP_VAR, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_POW, OP_NEG,
