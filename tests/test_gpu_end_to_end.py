@@ -107,3 +107,29 @@ def test_device_solution_norms_match_harness(msfec, pairing):
                 assert abs(dev[c, 2] - h ** 3 * (u_gpu ** 2).sum()) <= 1e-11 * dev[c, 2] and dev[c, 3] == 0.0
             if pairing == "Q":
                 assert dev[c, 2] == 0.0 and dev[c, 3] == 0.0
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_weight_scatter_matches_oracle_bases_at_three_refinements(msfec, pairing):
+    """a9 (set_global_weights, ned_rt_basis.cc:1156-1181) against the ORACLE's basis functions, not the library's own:
+    u_fine = sum_j w_j b_j with random weights at 3 local refinements, every fine DoF compared."""
+    L = 3
+    cells = mo.morton_cells(2)[[3, 40]]
+    ids = np.array([3, 40])
+    prob = oracle_problem(pairing, L)
+    bb = msfec.BasisBuilder(lib_problem(msfec, pairing, L), device=0).run(cells, ids)
+    k = mo.k_of(pairing)
+    k0 = {"Q": 8, "Q_NED": 8, "NED_RT": 12, "RT_DQ": 6}[pairing]
+    w = np.random.default_rng(5).standard_normal((2, k))
+    bb.set_global_weights(w)
+    p0 = _perm_to_oracle(bb, prob, 0, KINDS[pairing][0])
+    p1 = _perm_to_oracle(bb, prob, 1, KINDS[pairing][1]) if KINDS[pairing][1] else None
+    for c in range(2):
+        _, _, X0, X1, _ = mo.build_basis(prob, cells[c], int(ids[c]))
+        s_gpu, u_gpu = bb.get_fine_solution(c)
+        assert rel_err(s_gpu, (w[c, :k0] @ X0[:k0])[p0]) < 1e-9
+        if pairing == "RT_DQ":
+            assert rel_err(u_gpu, w[c, 6] * np.ones(prob.n ** 3)) < 1e-12
+        elif p1 is not None:
+            assert rel_err(u_gpu, (w[c, k0:] @ X1[k0:])[p1]) < 1e-9
+    bb.close()
