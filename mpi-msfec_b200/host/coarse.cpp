@@ -8,6 +8,7 @@
 #include <stdexcept>
 
 #include "../../include/msfec.h"
+#include "../../include/msfec_coarse.h"
 
 namespace msfec {
 
@@ -246,6 +247,19 @@ std::string CoarseProblem::solve() {
       }
       for (int c = 0; c < 2; ++c) B[a][c].ptr[li + 1] = (int32_t)B[a][c].col.size();
     }
+    if (device_ >= 0) {
+      // the same nested iteration on the rank's GPU (csrc/coarse_dev.cu); no silent fallback: a failure is an error
+      auto view = [](const Csr &M) { return msfec_coarse_csr{M.n_rows, M.n_cols, M.ptr.data(), M.col.data(), M.val.data()}; };
+      const msfec_coarse_csr v00 = view(B[0][0]), v01 = view(B[0][1]), v10 = view(B[1][0]), v11 = view(B[1][1]);
+      msfec_coarse_stats cs{};
+      const bool two = nb[1] > 0;
+      if (msfec_coarse_solve_device(device_, &v00, two ? &v01 : nullptr, two ? &v10 : nullptr, two ? &v11 : nullptr, bf.data(),
+                                    two ? bf.data() + nb[0] : nullptr, 1e-13, 1e-11, xf.data(), two ? xf.data() + nb[0] : nullptr, &cs))
+        throw std::runtime_error(std::string("coarse solve on the device: ") + msfec_coarse_last_error());
+      if (two) info << "Schur-complement CG on device " << device_ << ", " << cs.outer_iterations << " outer iterations, " << cs.inner_iterations << " inner CG iterations";
+      else info << "CG (Jacobi) on device " << device_ << " on the SPD coarse system, " << cs.inner_iterations << " iterations";
+      info << ", " << cs.kernel_launches << " kernel launches, " << cs.ms_device << " ms";
+    } else {
     std::vector<double> d0(nb[0]);
     for (int r = 0; r < nb[0]; ++r) {
       double d = 0;
@@ -288,6 +302,7 @@ std::string CoarseProblem::solve() {
       std::copy(sig.begin(), sig.end(), xf.begin());
       std::copy(u.begin(), u.end(), xf.begin() + nb[0]);
       info << "Schur-complement CG, " << outer << " outer iterations, " << inner_total << " inner CG iterations";
+    }
     }
   }
   std::fill(x_.begin(), x_.end(), 0.0);

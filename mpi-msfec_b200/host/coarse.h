@@ -12,10 +12,12 @@
 // vertices and boundary edges (q_ned_global.cc:175-207); Ned_RT / RT_DQ -- none (natural conditions,
 // ned_rt_global.cc:162-190, rt_dq_global.cc:154-182).
 //
-// Solver: Trilinos is not available here, so the system is solved on the host: dense LU with partial pivoting up to
-// a few thousand unknowns (exact: the parity tests), beyond that the reference's own scheme -- Schur-complement CG with
-// an inner CG on block (0,0) (ned_rt_global.cc:330-461), Q: plain CG -- with tolerances tightened from the reference's
-// 1e-6 so that the final solution is reproducible to 1e-8.
+// Solver: Trilinos is not available here.  Dense LU with partial pivoting up to a few thousand unknowns (exact: the parity
+// tests), beyond that the reference's own scheme -- Schur-complement CG with an inner CG on block (0,0)
+// (ned_rt_global.cc:330-461), Q: plain CG -- with tolerances tightened from the reference's 1e-6 so that the final
+// solution is reproducible to 1e-8.  The iteration runs on the rank's GPU when a device was set (set_device; the
+// drivers do: include/msfec_coarse.h, csrc/coarse_dev.cu -- C5's 205 920 unknowns: about a second instead of a minute on
+// one host core) and on the host otherwise (coarse_test, CPU tests).
 #pragma once
 #include <array>
 #include <cstdint>
@@ -44,6 +46,7 @@ class CoarseProblem {
   void cell_weights(long long cell, double *w) const;
   double residual() const { return residual_; }   // ||b - A x||_2 / ||b||_2 over the free unknowns
   void set_dense_limit(int n) { dense_limit_ = n; }
+  void set_device(int device) { device_ = device; }   // >= 0: the iterative solve runs on that GPU
 
  private:
   void ijk_of(long long cell, int &i, int &j, int &k) const;
@@ -60,6 +63,7 @@ class CoarseProblem {
   bool finalized_ = false;
   double residual_ = 0;
   int dense_limit_ = 6000;
+  int device_ = -1;
 };
 
 }  // namespace msfec

@@ -3,7 +3,9 @@
 // harness' scipy solve (tests/coarse_solve.py).
 //   input  (binary): int64 {pairing, global refinements, n_cells, dense_limit}, then per cell: int64 id, double M[k*k], double r[k]
 //   output (binary): double weights[n_cells][k] in input order
+// optional third argument: CUDA device for the iterative solve (include/msfec_coarse.h); default: host
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <iostream>
 #include <vector>
@@ -12,13 +14,14 @@
 #include "coarse.h"
 
 int main(int argc, char **argv) {
-  if (argc != 3) { std::cerr << "usage: coarse_test <in.bin> <out.bin>\n"; return 2; }
+  if (argc != 3 && argc != 4) { std::cerr << "usage: coarse_test <in.bin> <out.bin> [device]\n"; return 2; }
   try {
     std::ifstream in(argv[1], std::ios::binary);
     long long hdr[4];
     in.read((char *)hdr, sizeof(hdr));
     msfec::CoarseProblem cp((int)hdr[0], (int)hdr[1]);
     cp.set_dense_limit((int)hdr[3]);
+    if (argc == 4) cp.set_device(std::atoi(argv[3]));
     const int k = cp.k();
     std::vector<long long> ids(hdr[2]);
     std::vector<double> M((size_t)k * k), r(k);

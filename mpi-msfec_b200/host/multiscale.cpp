@@ -69,6 +69,15 @@ void Multiscale<PAIRING>::initialize_and_compute_basis() {
 template <int PAIRING>
 void Multiscale<PAIRING>::setup_system_matrix() {
   coarse_.reset(new CoarseProblem(PAIRING, parameters.n_refine_global));
+  // the nested coarse iteration runs on this rank's GPU (MSFEC_COARSE_SOLVER=host keeps it on the host cores;
+  // MSFEC_COARSE_DENSE_LIMIT: unknowns up to which the exact dense LU is used instead, default 6000)
+  {
+    const char *where = std::getenv("MSFEC_COARSE_SOLVER");
+    if (where && std::string(where) != "host" && std::string(where) != "device")
+      throw std::invalid_argument("MSFEC_COARSE_SOLVER must be host or device");
+    if (!where || std::string(where) == "device") coarse_->set_device(device_);
+    if (const char *lim = std::getenv("MSFEC_COARSE_DENSE_LIMIT")) coarse_->set_dense_limit(std::atoi(lim));
+  }
   if (rank_ == 0) {
     std::cout << "Number of active cells: " << n_global_cells_ << std::endl
               << "Total number of cells: " << ((8 * n_global_cells_ - 1) / 7) << " (on " << parameters.n_refine_global + 1 << " levels)" << std::endl

@@ -142,3 +142,57 @@ def test_driver_two_ranks_over_nccl(msfec, host_built, tmp_path):
     w1 = np.fromfile(tmp_path / "a" / "out" / "Ned_RT_coarse_weights.bin", dtype=np.uint8)[16:].view(np.float64)
     w2 = np.fromfile(d / "Ned_RT_coarse_weights.bin", dtype=np.uint8)[16:].view(np.float64)
     assert np.abs(w1 - w2).max() <= 1e-12 * np.abs(w1).max()
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_coarse_solve_on_device_matches_harness(host_built, tmp_path, pairing):
+    """include/msfec_coarse.h: the coarse system's nested iteration on the GPU (Schur-complement CG + inner CG; Q: CG) gives the
+    harness' scipy weights (1e-7, the bar of the host iteration in tests/test_host_driver.py) and the host iteration's own
+    result to 1e-9; 512 coarse cells (3 global refinements), oracle element matrices at 1 local refinement."""
+    import coarse_solve as cs
+    from common import oracle_problem
+    g = 3
+    cells = mo.morton_cells(g)
+    prob = oracle_problem(pairing, 1)
+    M, r = [], []
+    for c in range(len(cells)):
+        Mc, rc, *_ = mo.build_basis(prob, cells[c], c)
+        M.append(Mc); r.append(rc)
+    M = np.array(M); r = np.array(r)
+    n, k = r.shape
+    with open(tmp_path / "in.bin", "wb") as f:
+        f.write(np.array([PAIRING[pairing], g, n, 0], np.int64).tobytes())          # dense limit 0: iterate
+        for c in range(n):
+            f.write(np.array([c], np.int64).tobytes()); f.write(M[c].tobytes()); f.write(r[c].tobytes())
+    exe = os.path.join(host_built, "coarse_test")
+    dev = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "dev.bin"), "0"], capture_output=True, text=True, timeout=600)
+    assert dev.returncode == 0 and "on device 0" in dev.stdout, dev.stdout + dev.stderr
+    host = subprocess.run([exe, str(tmp_path / "in.bin"), str(tmp_path / "host.bin")], capture_output=True, text=True, timeout=600)
+    assert host.returncode == 0 and "on device" not in host.stdout, host.stdout + host.stderr
+    print(dev.stdout.strip()); print(host.stdout.strip())
+    w_dev = np.fromfile(tmp_path / "dev.bin").reshape(n, k)
+    w_host = np.fromfile(tmp_path / "host.bin").reshape(n, k)
+    ref = cs.solve_coarse(pairing, g, cells, M, r)
+    assert np.abs(w_dev - ref).max() <= 1e-7 * np.abs(ref).max()
+    assert np.abs(w_dev - w_host).max() <= 1e-9 * np.abs(ref).max()
+    resid = float(re.search(r"relative residual ([0-9.e+-]+)", dev.stdout).group(1))
+    assert resid < 1e-8
+
+
+def test_driver_iterates_on_the_device_by_default(host_built, tmp_path):
+    """The driver hands the coarse iteration to its GPU when the system is beyond the dense-LU size (forced here with
+    MSFEC_COARSE_DENSE_LIMIT=0) and prints the same norms as the dense-LU run to 1e-8; MSFEC_COARSE_SOLVER=host keeps it on
+    the host."""
+    (tmp_path / "a").mkdir(); (tmp_path / "b").mkdir(); (tmp_path / "c").mkdir()
+    prm_a, _ = _small_prm(tmp_path / "a", "NED_RT")
+    prm_b, _ = _small_prm(tmp_path / "b", "NED_RT")
+    prm_c, _ = _small_prm(tmp_path / "c", "NED_RT")
+    lu = _run_driver(host_built, "NED_RT", prm_a, {})
+    dev = _run_driver(host_built, "NED_RT", prm_b, {"MSFEC_COARSE_DENSE_LIMIT": "0"})
+    hst = _run_driver(host_built, "NED_RT", prm_c, {"MSFEC_COARSE_DENSE_LIMIT": "0", "MSFEC_COARSE_SOLVER": "host"})
+    assert "dense LU" in lu and "Schur-complement CG on device 0" in dev and "Schur-complement CG, " in hst
+    # test-01's right-hand side is a pure gradient: sigma vanishes identically (norms ~1e-15 .. 1e-11), so the bar is
+    # relative to the largest norm
+    tol = dict(rtol=1e-8, atol=1e-9 * _norms(lu).max())
+    assert np.allclose(_norms(dev), _norms(lu), **tol)
+    assert np.allclose(_norms(hst), _norms(lu), **tol)

@@ -89,3 +89,29 @@ def test_driver_cli_errors(host_built, tmp_path):
     assert subprocess.run([exe], capture_output=True).returncode == 1
     r = subprocess.run([exe, "-p", str(tmp_path / "missing.prm")], capture_output=True, text=True)
     assert r.returncode == 1 and "Exception on processing" in r.stderr
+
+
+def test_coarse_device_solver_exports_and_fails_loudly_without_gpu(host_built):
+    """libmsfec_b200.so exports what include/msfec_coarse.h declares; without a device the call is an error (no CPU fallback
+    inside it -- the host solver of coarse.cpp is a separate, explicit choice)."""
+    hdr = open(os.path.join(ROOT, "include", "msfec_coarse.h")).read()
+    declared = sorted(set(re.findall(r"\b(msfec_coarse_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared == ["msfec_coarse_last_error", "msfec_coarse_solve_device"]
+    lib = C.CDLL(os.path.join(ROOT, "mpi-msfec_b200", "libmsfec_b200.so"))
+    for name in declared:
+        assert hasattr(lib, name), name
+
+    class Csr(C.Structure):
+        _fields_ = [("n_rows", C.c_int32), ("n_cols", C.c_int32), ("ptr", C.POINTER(C.c_int32)), ("col", C.POINTER(C.c_int32)),
+                    ("val", C.POINTER(C.c_double))]
+    ptr = (C.c_int32 * 3)(0, 1, 2); col = (C.c_int32 * 2)(0, 1); val = (C.c_double * 2)(2.0, 4.0)
+    A = Csr(2, 2, ptr, col, val)
+    b = (C.c_double * 2)(2.0, 4.0); x = (C.c_double * 2)()
+    lib.msfec_coarse_last_error.restype = C.c_char_p
+    lib.msfec_coarse_solve_device.argtypes = [C.c_int, C.POINTER(Csr), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
+                                              C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p]
+    if not os.path.exists("/dev/nvidiactl"):
+        assert lib.msfec_coarse_solve_device(0, C.byref(A), None, None, None, b, None, 1e-13, 1e-11, x, None, None) != 0
+        assert b"no CUDA device" in lib.msfec_coarse_last_error()
+    assert lib.msfec_coarse_solve_device(0, None, None, None, None, b, None, 1e-13, 1e-11, x, None, None) != 0
+    assert b"null argument" in lib.msfec_coarse_last_error()
