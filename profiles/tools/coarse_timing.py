@@ -1,5 +1,5 @@
 """Times the global coarse solve of the host driver (host/coarse.cpp) on the host cores and on the GPU (include/msfec_coarse.h):
-python profiles/tools/coarse_timing.py <PAIRING> <global refinements> [host|device|both].  Element matrices come from the oracle
+python profiles/tools/coarse_timing.py <PAIRING> <global refinements> [host|device|both] [dense-LU limit, default 6000].  Element matrices come from the oracle
 at 1 local refinement with the rough random field of C5 (cheap; only the coarse system's size and conditioning matter here)."""
 import os
 import subprocess
@@ -16,6 +16,7 @@ from oracle import msfec_oracle as mo  # noqa: E402
 
 PAIRING = {"Q": 0, "Q_NED": 1, "NED_RT": 2, "RT_DQ": 3}
 pairing = sys.argv[1]; g = int(sys.argv[2]); which = sys.argv[3] if len(sys.argv) > 3 else "both"
+dense_limit = int(sys.argv[4]) if len(sys.argv) > 4 else 6000
 cells = mo.morton_cells(g)
 prob = oracle_problem(pairing, 1, random_seed=20261017)
 
@@ -33,7 +34,7 @@ if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, ".scratch"), exist_ok=True)
     inp = os.path.join(ROOT, ".scratch", "coarse_in.bin")
     with open(inp, "wb") as f:
-        f.write(np.array([PAIRING[pairing], g, len(cells), 6000], np.int64).tobytes())
+        f.write(np.array([PAIRING[pairing], g, len(cells), dense_limit], np.int64).tobytes())
         for c in range(len(cells)):
             f.write(np.array([c], np.int64).tobytes()); f.write(out[c][0].tobytes()); f.write(out[c][1].tobytes())
     exe = os.path.join(ROOT, "mpi-msfec_b200", "host", "coarse_test")
