@@ -111,7 +111,8 @@ typedef struct msfec_stats {
   double direct_flops;           /* FP64 tensor-core flops of the build: trailing updates (lower triangle) + solves */
   double direct_flops_timed;     /* flops of the k_direct_update_s launches that were bracketed by events           */
   double direct_ms_update;       /* summed device time of those launches                                            */
-  int32_t solver;                /* 0 = batched MINRES, 1 = batched block LDL^T (band), 2 = batched multifrontal LDL^T */
+  int32_t solver;                /* 0 = batched MINRES, 1 = batched block LDL^T (band), 2 = batched multifrontal LDL^T,
+                                    3 = none (0 local refinements: no interior unknowns)                              */
   int32_t direct_timed_launches; /* number of event-bracketed k_direct_update_s launches                             */
   /* multifrontal path */
   double mf_flops;               /* FP64 flops of the front kernels of the build (padded front sizes)                */

@@ -202,14 +202,22 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
   if (!p || !out) return set_error(nullptr, MSFEC_EINVAL, "null argument");
   *out = nullptr;
   if (pairing_k(p->pairing) < 0) return set_error(nullptr, MSFEC_EINVAL, "unknown pairing");
-  if (p->n_refine_local < 1 || p->n_refine_local > 6)
-    return set_error(nullptr, MSFEC_EINVAL, "local refinements must be in [1, 6]");
+  // 0 local refinements: the coarse cell is its own fine grid, there is nothing to solve and the "multiscale" basis is the
+  // standard lowest-order basis -- what the fine-grid comparator of the host driver builds its element matrices with
+  if (p->n_refine_local < 0 || p->n_refine_local > 6)
+    return set_error(nullptr, MSFEC_EINVAL, "local refinements must be in [0, 6]");
   msfec_ctx *ctx = nullptr;
   try {
     ctx = new msfec_ctx();
     ctx->topo = build_topology(p->pairing, 1 << p->n_refine_local);
     make_spec(*p, ctx->topo, ctx->spec);
-    {
+    // no interior unknowns (RT_DQ at n = 1: only the pinned cell unknown): no local solve, no factorisation plans
+    const bool no_interior = ctx->topo.NI == 0 || (p->pairing == MSFEC_RT_DQ && p->n_refine_local == 0);
+    if (no_interior) {
+      ctx->plan = DirectPlan();
+      ctx->mf = MfPlan();
+      ctx->mf.why = "no interior unknowns";
+    } else {
       // RT_DQ: a layer block alone is a pure-Neumann sub-problem (singular pivot); keep layer + plane together.
       // Otherwise: layers/planes, or nested dissection when its symbolic flop count is lower (from n = 16 on).
       int ordering = p->pairing == MSFEC_RT_DQ ? 1 : 0;
@@ -238,8 +246,10 @@ int msfec_create(int device, const msfec_problem *p, msfec_ctx **out) {
       ctx->plan = have ? std::move(plan) : DirectPlan();
     }
     // multifrontal plan (fronts resident in shared memory): feasible up to 3 local refinements; the engine prefers it
-    try { ctx->mf = build_mf_plan(ctx->topo); }
-    catch (const std::exception &ex) { ctx->mf = MfPlan(); ctx->mf.why = ex.what(); }
+    if (!no_interior) {
+      try { ctx->mf = build_mf_plan(ctx->topo); }
+      catch (const std::exception &ex) { ctx->mf = MfPlan(); ctx->mf.why = ex.what(); }
+    }
     if (device >= 0) ctx->engine = engine_create(device, ctx->spec, ctx->topo, ctx->plan, ctx->mf);
     *out = ctx;
     return MSFEC_OK;

@@ -973,6 +973,7 @@ class Engine {
   // solver of the local problems: 0 batched MINRES, 1 banded block LDL^T, 2 multifrontal LDL^T (msfec_stats.solver)
   int solver_ = 0;
   bool use_mf_ = false;
+  bool no_solve_ = false;      // 0 local refinements: no interior unknowns, nothing to solve
   void select_solver();
   void upload_mf();
   void free_mf();
@@ -1207,6 +1208,10 @@ void Engine::launch_residual_check(int groups, double kscale, int pinned_row) {
 // factorisation that exists for the problem size -- multifrontal (fronts in shared memory, up to 3 local refinements),
 // else the banded block LDL^T -- and batched MINRES only when there is no plan (memory fallback).
 void Engine::select_solver() {
+  // 0 local refinements: every fine unknown lies on the boundary of the coarse cell (RT_DQ: plus the pinned cell unknown) --
+  // the basis is the boundary data itself, no solver is set up and build() skips preconditioner, lifting and solve
+  no_solve_ = T_.NI == 0 || (T_.pairing == MSFEC_RT_DQ && T_.n == 1);
+  if (no_solve_) { solver_ = 0; use_direct_ = use_mf_ = false; residual_full_ = false; return; }
   int want = spec_.p.solver;
   if (const char *e = std::getenv("MSFEC_FORCE_SOLVER")) {
     const std::string v = e;
@@ -1656,14 +1661,17 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
     }
     k_assemble_slots<<<dim3((T_.asm_rhs.n_slots + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
         asmrhs_.dev, T_.nC, d_fr_, std::pow(h, T_.asm_rhs.h_exponent) / 8.0, d_grhs_, T_.asm_rhs.n_slots, 0);
-    if (solver_ == 0) k_build_precond<<<dim3((T_.NI + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
+    if (solver_ == 0 && !no_solve_) k_build_precond<<<dim3((T_.NI + 7) / 8, groups), dim3(kLanes, 8), 0, stream_>>>(
         T_.blk[0].n_int, T_.NI, n_slots_, d_diag0_, d_diag1_, kint_.dev, kscale, d_vals_, d_minv_);
     CUDA_OK(cudaEventRecord(ev_[1], stream_));
-    k_lift_rhs<<<dim3((T_.NI + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(
+    if (!no_solve_) k_lift_rhs<<<dim3((T_.NI + 3) / 4, groups), dim3(kLanes, 4), 0, stream_>>>(
         lift_.dev, T_.NI, T_.NB, T_.k_solve, n_slots_, kscale, f1scale, d_vals_, d_G_, d_F1_, d_vec_[2]);
-    launches_ += 3;
+    launches_ += no_solve_ ? 1 : 3;
     CUDA_OK(cudaEventRecord(ev_[2], stream_));
-    if (use_mf_) solve_mf_batch(groups, nb, kscale);
+    if (no_solve_) {
+      // interior "solution": empty, or the pinned unknown of RT_DQ (0; finalize_basis sets u := 1)
+      if (T_.NI > 0) CUDA_OK(cudaMemsetAsync(d_vec_[7], 0, (size_t)groups * T_.NI * T_.k_solve * kLanes * sizeof(double), stream_));
+    } else if (use_mf_) solve_mf_batch(groups, nb, kscale);
     else if (use_direct_) solve_direct_batch(groups, nb, kscale, st);
     else { const int itb = solve_batch(groups, nb, kscale, st, ms_spmm); total_it += itb; cell_iters_ += (double)itb * nb; }
     CUDA_OK(cudaEventRecord(ev_[3], stream_));
@@ -1743,7 +1751,7 @@ int Engine::build(int n_cells, const double *corners, const int64_t *cell_ids, d
   st.krylov_spmm_launches = total_it;
   st.krylov_ms_spmm = spmm_samples_ ? ms_spmm / spmm_samples_ : 0.0;   // mean duration of one SpMM launch
   st.direct_flops = direct_flops_; st.direct_flops_timed = direct_flops_timed_; st.direct_ms_update = direct_ms_update_;
-  st.direct_update_launches = direct_update_launches_; st.solver = solver_;
+  st.direct_update_launches = direct_update_launches_; st.solver = no_solve_ ? 3 : solver_;
   if (use_mf_) {
     for (size_t i = 0; i + 3 <= mf_marks_used_; i += 3) {
       float ms = 0;

@@ -55,14 +55,55 @@ bool ms_control_flag(const std::string &file, const std::string &key, bool dflt)
   }
   return value;
 }
+
+// "set <key> = value" inside the nested subsections `path` (exact nesting)
+std::string prm_value(const std::string &file, const std::vector<std::string> &path, const std::string &key, const std::string &dflt) {
+  std::ifstream in(file);
+  std::string line, value = dflt;
+  std::vector<std::string> stack;
+  auto trim = [](std::string s) {
+    const size_t b = s.find_first_not_of(" \t\r"), e = s.find_last_not_of(" \t\r");
+    return b == std::string::npos ? std::string() : s.substr(b, e - b + 1);
+  };
+  while (std::getline(in, line)) {
+    line = trim(line.substr(0, line.find('#')));
+    if (line.rfind("subsection", 0) == 0) stack.push_back(trim(line.substr(10)));
+    else if (line == "end") { if (!stack.empty()) stack.pop_back(); }
+    else if (line.rfind("set ", 0) == 0 && stack == path) {
+      const size_t eq = line.find('=');
+      if (eq != std::string::npos && trim(line.substr(4, eq - 4)) == key) value = trim(line.substr(eq + 1));
+    }
+  }
+  return value;
+}
 }  // namespace
 
-ParametersMs::ParametersMs(const std::string &prm_filename, int pairing) {
+ParametersMs::ParametersMs(const std::string &prm_filename, int pairing, bool standard_method) : standard(standard_method) {
   if (msfec_problem_from_prm(prm_filename.c_str(), pairing, &problem))
     throw std::runtime_error(std::string("parameter file: ") + msfec_last_error(nullptr));
-  filename_output = ms_top_level_value(prm_filename, "filename output", filename_output);   // ned_rt_parameters.cc:226-236
-  dirname_output = ms_top_level_value(prm_filename, "dirname output", dirname_output);
-  write_first_basis = ms_control_flag(prm_filename, "write first basis", false);
+  if (standard) {
+    // ParametersStd (ned_rt_parameters.cc:8-125): defaults n_refine = 3, compute solution = true
+    const std::vector<std::string> top{"Standard method parameters"}, mesh{top[0], "Mesh"}, flow{top[0], "Control flow"};
+    static const char *dflt_name[4] = {"Q_Std", "Q_NED_Std", "NED_RT_Std", "RT_DQ_Std"};
+    const std::string r = prm_value(prm_filename, mesh, "refinements", "3");
+    char *end = nullptr;
+    const long refinements = std::strtol(r.c_str(), &end, 10);
+    if (end == r.c_str() || *end != 0 || refinements < 1 || refinements > 8)
+      throw std::runtime_error("parameter file: 'Standard method parameters/Mesh/refinements' must be an integer in [1, 8]");
+    problem.n_refine_global = (int)refinements;
+    problem.n_refine_local = 0;
+    problem.verbose_basis = 0;
+    compute_solution = prm_value(prm_filename, flow, "compute solution", "true") == "true";
+    verbose = prm_value(prm_filename, flow, "verbose", "false") == "true";
+    filename_output = prm_value(prm_filename, top, "filename output", dflt_name[pairing]);
+    dirname_output = prm_value(prm_filename, top, "dirname output", dirname_output);
+    write_first_basis = false;
+  } else {
+    filename_output = ms_top_level_value(prm_filename, "filename output", filename_output);   // ned_rt_parameters.cc:226-236
+    dirname_output = ms_top_level_value(prm_filename, "dirname output", dirname_output);
+    write_first_basis = ms_control_flag(prm_filename, "write first basis", false);
+    compute_solution = ms_control_flag(prm_filename, "compute solution", true);
+  }
   n_refine_global = problem.n_refine_global;
   n_refine_local = problem.n_refine_local;
   verbose_basis = problem.verbose_basis != 0;

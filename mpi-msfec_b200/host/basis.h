@@ -22,8 +22,13 @@ struct ParametersMs {          // subset of NedRT::ParametersMs the basis path r
   std::string filename_output = "Ms", dirname_output = "data-output";
   bool verbose = false, verbose_basis = false, prevent_output = false, write_first_basis = false;
   int n_refine_global = 2, n_refine_local = 1;
+  bool compute_solution = true;   // "Control flow / compute solution" of the section read
+  bool standard = false;          // true: these are the reference's ParametersStd (ned_rt_parameters.cc:8-125)
   // Reads the reference's .prm verbatim (ned_rt_parameters.cc:131-257).  Throws std::runtime_error.
-  ParametersMs(const std::string &prm_filename, int pairing);
+  // standard = true reads `subsection Standard method parameters` instead (the fine-grid comparator XStd): its
+  // `Mesh / refinements` become the global refinements, there are 0 local refinements (every cell of that mesh is its own
+  // fine grid: the basis build returns the standard element matrices), its output names replace the multiscale ones.
+  ParametersMs(const std::string &prm_filename, int pairing, bool standard = false);
   ~ParametersMs();
   ParametersMs(const ParametersMs &) = delete;
   ParametersMs &operator=(const ParametersMs &) = delete;

@@ -25,17 +25,19 @@ const char *block_names(int pairing, int blk) {
 }  // namespace
 
 template <int PAIRING>
-Multiscale<PAIRING>::Multiscale(const ParametersMs &prm, const std::string &prm_file, int rank, int world, int device, const char *name)
-    : parameters(prm), parameter_filename(prm_file), rank_(rank), world_(world), device_(device), name_(name) {
+Multiscale<PAIRING>::Multiscale(const ParametersMs &prm, const std::string &prm_file, int rank, int world, int device, const char *name,
+                                msfec_comm *shared_comm)
+    : parameters(prm), parameter_filename(prm_file), rank_(rank), world_(world), device_(device), name_(name), comm_(shared_comm) {
   // NCCL communicator for the two cross-rank steps; a single rank needs none (MSFEC_NCCL=1 creates it anyway)
-  if (world_ > 1 || (std::getenv("MSFEC_NCCL") && std::atoi(std::getenv("MSFEC_NCCL")) != 0)) {
+  if (!comm_ && (world_ > 1 || (std::getenv("MSFEC_NCCL") && std::atoi(std::getenv("MSFEC_NCCL")) != 0))) {
     if (msfec_comm_create(rank_, world_, device_, &comm_)) throw std::runtime_error(std::string("NCCL communicator: ") + msfec_comm_last_error());
+    owns_comm_ = true;
     if (rank_ == 0) std::cout << "NCCL communicator over " << world_ << " rank(s) created (one rank per GPU)." << std::endl;
   }
 }
 
 template <int PAIRING>
-Multiscale<PAIRING>::~Multiscale() { msfec_comm_destroy(comm_); }
+Multiscale<PAIRING>::~Multiscale() { if (owns_comm_) msfec_comm_destroy(comm_); }
 
 // hyper_cube + refine_global; ownership = contiguous chunks of the z-order (ned_rt_global.cc:36-46, 12-15)
 template <int PAIRING>
@@ -58,7 +60,7 @@ void Multiscale<PAIRING>::initialize_and_compute_basis() {
   for (auto &kv : cell_basis_map) kv.second.run();
   t_basis_ = now() - t0;
   const msfec_stats &st = batch_->stats();
-  const char *solver = st.solver == 2 ? "multifrontal LDL^T" : st.solver == 1 ? "banded block LDL^T" : "MINRES";
+  const char *solver = st.solver == 3 ? "none (0 local refinements)" : st.solver == 2 ? "multifrontal LDL^T" : st.solver == 1 ? "banded block LDL^T" : "MINRES";
   std::cout << "[rank " << rank_ << "] " << name_ << " basis initialization and computation: " << (hi_ - lo_) << " cells in " << t_basis_
             << " s (device " << st.ms_total << " ms; assemble " << st.ms_assemble << ", lift " << st.ms_lift << ", solve "
             << st.ms_solve << ", coarse matrices " << st.ms_gram << "; solver " << solver << ", max its " << st.iterations_max
@@ -162,7 +164,7 @@ void Multiscale<PAIRING>::compute_norms() {
   if (rank_ == 0) {
     const char *semi0 = PAIRING == MSFEC_NED_RT ? "H(curl)" : PAIRING == MSFEC_RT_DQ ? "H(div)" : "H1";
     const char *semi1 = PAIRING == MSFEC_NED_RT ? "H(div)" : "H(curl)";
-    std::printf("   Multiscale solution norms: ||%s||_L2 = %.15e  |%s|_%s = %.15e", block_names(PAIRING, 0), norms_[0], block_names(PAIRING, 0), semi0, norms_[1]);
+    std::printf("   %s solution norms: ||%s||_L2 = %.15e  |%s|_%s = %.15e", parameters.standard ? "Standard" : "Multiscale", block_names(PAIRING, 0), norms_[0], block_names(PAIRING, 0), semi0, norms_[1]);
     if (PAIRING != MSFEC_Q) {
       std::printf("  ||u||_L2 = %.15e", norms_[2]);
       if (PAIRING != MSFEC_RT_DQ) std::printf("  |u|_%s = %.15e", semi1, norms_[3]);
@@ -188,6 +190,8 @@ void Multiscale<PAIRING>::output_results() {
   // MSFEC_MAX_OUTPUT_CELLS limits the number of per-cell files a rank writes (the reference writes all of them)
   long long limit = std::getenv("MSFEC_MAX_OUTPUT_CELLS") ? std::atoll(std::getenv("MSFEC_MAX_OUTPUT_CELLS")) : -1;
   long long written = 0;
+  // the fine-grid comparator has no fine grid below its cells: one file per rank and the .pvtu record (ned_rt_ref.cc:699-730)
+  if (parameters.standard) limit = 0;
   for (auto &kv : cell_basis_map) {
     if (limit >= 0 && written >= limit) break;
     kv.second.output_global_solution_in_cell();
@@ -281,8 +285,10 @@ void Multiscale<PAIRING>::output_results() {
         filenames_on_cell.push_back(parameters.filename_output + "." + int_to_string(r, 5) + ".cell-" + CellId(id, g).to_string() + ".vtu");
       }
     }
+    if (!parameters.standard) {
     const std::string filename_master = parameters.filename_output + "_fine_refine-" + int_to_string(g, 2) + "-" + int_to_string(parameters.n_refine_local, 2) + ".pvtu";
     pvtu(parameters.dirname_output + "/" + filename_master, filenames_on_cell, false);
+    }
   }
   t_output_ = now() - t0;
 }
@@ -290,9 +296,15 @@ void Multiscale<PAIRING>::output_results() {
 // ned_rt_global.cc:704-771
 template <int PAIRING>
 void Multiscale<PAIRING>::run() {
+  if (!parameters.compute_solution) {
+    // ned_rt_ref.cc:736-742 / ned_rt_global.cc:707-713
+    if (rank_ == 0) std::cout << "Run of " << (parameters.standard ? "standard" : "multiscale") << " problem is explicitly disabled in parameter file." << std::endl;
+    return;
+  }
   if (rank_ == 0)
     std::cout << "MsFEC_" << name_ << ": running on " << world_ << " rank(s), one GPU each" << std::endl
-              << "===========================================" << std::endl << "Solving >> MULTISCALE << problem in 3D." << std::endl;
+              << "===========================================" << std::endl
+              << "Solving >> " << (parameters.standard ? "STANDARD" : "MULTISCALE") << " << problem in 3D." << std::endl;
   make_grid();
   initialize_and_compute_basis();
   setup_system_matrix();
@@ -343,33 +355,6 @@ template class Multiscale<MSFEC_NED_RT>;
 template class Multiscale<MSFEC_RT_DQ>;
 
 // Mirrors source/main_ned_rt.cxx:15-117: parse "-p <prm>", construct XMultiscale, run(), catch-all.
-// `set compute solution = true` inside `subsection Standard method parameters` (any nesting below it)
-static bool std_solution_requested(const std::string &prm_file) {
-  std::ifstream in(prm_file);
-  std::string line;
-  int depth = 0, std_depth = -1;
-  auto trim = [](std::string t) {
-    const size_t h = t.find('#');
-    if (h != std::string::npos) t.erase(h);
-    const size_t a = t.find_first_not_of(" \t\r"), b = t.find_last_not_of(" \t\r");
-    return a == std::string::npos ? std::string() : t.substr(a, b - a + 1);
-  };
-  while (std::getline(in, line)) {
-    const std::string t = trim(line);
-    if (t.rfind("subsection", 0) == 0) {
-      if (std_depth < 0 && t.find("Standard method parameters") != std::string::npos) std_depth = depth;
-      ++depth;
-    } else if (t == "end") {
-      --depth;
-      if (depth == std_depth) std_depth = -1;
-    } else if (std_depth >= 0 && t.rfind("set", 0) == 0 && t.find("compute solution") != std::string::npos) {
-      const size_t eq = t.find('=');
-      if (eq != std::string::npos && trim(t.substr(eq + 1)) == "true") return true;
-    }
-  }
-  return false;
-}
-
 int driver_main(int argc, char **argv, int pairing, const char *name) {
   try {
     std::string prm_file;
@@ -385,17 +370,34 @@ int driver_main(int argc, char **argv, int pairing, const char *name) {
     const int world = env_int("OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "WORLD_SIZE", 1);
     const int device = env_int("OMPI_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "LOCAL_RANK", 0);
     ParametersMs prm(prm_file, pairing);
-    // The reference's main_*.cxx first runs the fine-grid comparator (*Std, `Standard method parameters`) and then the multiscale
-    // method.  The comparator is not part of this build: say so instead of silently skipping it.
-    if (rank == 0 && std_solution_requested(prm_file))
-      std::cout << "Note: `Standard method parameters / compute solution = true`: the fine-grid comparator (" << name
-                << "Std of the reference) is not part of this build and is skipped; running the multiscale method." << std::endl;
-    switch (pairing) {
-      case MSFEC_Q: { Multiscale<MSFEC_Q> ms(prm, prm_file, rank, world, device, name); ms.run(); break; }
-      case MSFEC_Q_NED: { Multiscale<MSFEC_Q_NED> ms(prm, prm_file, rank, world, device, name); ms.run(); break; }
-      case MSFEC_NED_RT: { Multiscale<MSFEC_NED_RT> ms(prm, prm_file, rank, world, device, name); ms.run(); break; }
-      default: { Multiscale<MSFEC_RT_DQ> ms(prm, prm_file, rank, world, device, name); ms.run(); break; }
+    // one NCCL communicator for both runs (a single rank needs none; MSFEC_NCCL=1 creates it anyway)
+    msfec_comm *comm = nullptr;
+    if (world > 1 || (std::getenv("MSFEC_NCCL") && std::atoi(std::getenv("MSFEC_NCCL")) != 0)) {
+      if (msfec_comm_create(rank, world, device, &comm)) throw std::runtime_error(std::string("NCCL communicator: ") + msfec_comm_last_error());
+      if (rank == 0) std::cout << "NCCL communicator over " << world << " rank(s) created (one rank per GPU)." << std::endl;
     }
+    struct CommGuard { msfec_comm *c; ~CommGuard() { msfec_comm_destroy(c); } } guard{comm};
+    auto run_one = [&](const ParametersMs &P, const std::string &label) {
+      switch (pairing) {
+        case MSFEC_Q: { Multiscale<MSFEC_Q> ms(P, prm_file, rank, world, device, label.c_str(), comm); ms.run(); break; }
+        case MSFEC_Q_NED: { Multiscale<MSFEC_Q_NED> ms(P, prm_file, rank, world, device, label.c_str(), comm); ms.run(); break; }
+        case MSFEC_NED_RT: { Multiscale<MSFEC_NED_RT> ms(P, prm_file, rank, world, device, label.c_str(), comm); ms.run(); break; }
+        default: { Multiscale<MSFEC_RT_DQ> ms(P, prm_file, rank, world, device, label.c_str(), comm); ms.run(); break; }
+      }
+    };
+    // The reference's main_*.cxx (main_ned_rt.cxx:66-82) first runs the fine-grid comparator XStd (`Standard method
+    // parameters`), then the multiscale method.  MSFEC_STD_MAX_REFINEMENTS (default 6: 64^3 cells) bounds the comparator's mesh.
+    {
+      ParametersMs std_prm(prm_file, pairing, /*standard=*/true);
+      const int max_ref = std::getenv("MSFEC_STD_MAX_REFINEMENTS") ? std::atoi(std::getenv("MSFEC_STD_MAX_REFINEMENTS")) : 6;
+      if (std_prm.compute_solution && std_prm.n_refine_global > max_ref) {
+        if (rank == 0) std::cout << "Note: the fine-grid comparator (" << name << "Std) asks for " << std_prm.n_refine_global
+                                 << " refinements, MSFEC_STD_MAX_REFINEMENTS = " << max_ref << ": skipped." << std::endl;
+      } else {
+        run_one(std_prm, std::string(name) + "Std");
+      }
+    }
+    run_one(prm, name);
     return 0;
   } catch (std::exception &exc) {
     std::cerr << "\n----------------------------------------------------\nException on processing:\n" << exc.what()

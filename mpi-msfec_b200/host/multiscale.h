@@ -22,8 +22,13 @@ template <int PAIRING>
 class Multiscale {
  public:
   using Basis = BasisT<PAIRING>;
+  // shared_comm: an NCCL communicator owned by the caller (the driver runs the fine-grid comparator and the multiscale
+  // method on one communicator); nullptr: create one when world > 1.
+  // parameters.standard: this object is the reference's XStd (source/Ned_RT/ned_rt_ref.cc and siblings): the same pipeline on
+  // the mesh refined `Standard method parameters / Mesh / refinements` times with 0 local refinements -- the basis build
+  // returns the standard lowest-order element matrices of every cell, the coarse solve IS the fine-grid solve.
   Multiscale(const ParametersMs &parameters, const std::string &parameter_filename, int rank, int world, int device,
-             const char *name);
+             const char *name, msfec_comm *shared_comm = nullptr);
   ~Multiscale();
   void run();
 
@@ -47,6 +52,7 @@ class Multiscale {
   int rank_, world_, device_;
   std::string name_;
   msfec_comm *comm_ = nullptr;
+  bool owns_comm_ = false;
   long long n_global_cells_ = 0, lo_ = 0, hi_ = 0;
   CellId first_cell_;
   std::shared_ptr<BasisBatch> batch_;

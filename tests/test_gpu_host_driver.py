@@ -30,8 +30,11 @@ def host_built(msfec):
     return HOST
 
 
-def _small_prm(tmp_path, pairing, L=2, g=2, verbose_basis=False):
+def _small_prm(tmp_path, pairing, L=2, g=2, verbose_basis=False, std_refinements=2):
     txt = open(prm_path(pairing)).read()
+    # the fine-grid comparator (`Standard method parameters`, shipped: 6 refinements = 64^3 cells) on a small mesh too
+    assert "set refinements = 6" in txt and txt.count("set compute solution = true") == 2
+    txt = txt.replace("set refinements = 6", f"set refinements = {std_refinements}")
     txt = re.sub(r"set local refinements = \d+", f"set local refinements = {L}", txt)
     txt = re.sub(r"set global refinements = \d+", f"set global refinements = {g}", txt)
     txt = re.sub(r"set dirname output = \S+", f"set dirname output = {tmp_path}/out", txt)
@@ -78,9 +81,10 @@ def test_driver_end_to_end_single_rank(msfec, host_built, tmp_path, pairing):
     prm, fname = _small_prm(tmp_path, pairing, verbose_basis=True)
     out = _run_driver(host_built, pairing, prm, {"MSFEC_NCCL": "1"})
     assert "NCCL communicator over 1 rank(s)" in out and "Outer solver completed." in out
-    # the shipped .prm files ask for the fine-grid comparator too (`Standard method parameters / compute solution = true`): it is out
-    # of scope here and the driver says so
-    assert "fine-grid comparator" in out and "is skipped" in out
+    # the shipped .prm files ask for the fine-grid comparator too (`Standard method parameters / compute solution = true`): it runs
+    # first, as in the reference's main (test_standard_method_matches_oracle checks its result)
+    assert out.index("Solving >> STANDARD << problem in 3D.") < out.index("Solving >> MULTISCALE << problem in 3D.")
+    assert "Standard solution norms" in out
     assert len(re.findall(r"Solving for basis in cell   0_2:\d\d   \[machine: .* \| rank: 0\]   \.\.\.\.\.done in", out)) == 64
     d = tmp_path / "out"
     name = EXE[pairing][6:]
@@ -196,3 +200,41 @@ def test_driver_iterates_on_the_device_by_default(host_built, tmp_path):
     tol = dict(rtol=1e-8, atol=1e-9 * _norms(lu).max())
     assert np.allclose(_norms(dev), _norms(lu), **tol)
     assert np.allclose(_norms(hst), _norms(lu), **tol)
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_standard_method_matches_oracle(host_built, tmp_path, pairing):
+    """The fine-grid comparator XStd of the reference (source/Ned_RT/ned_rt_ref.cc and siblings; `Standard method parameters` of
+    the .prm): the driver runs it as the same pipeline with 0 local refinements on the mesh refined `refinements` times -- the
+    device returns the standard lowest-order element matrices, the coarse solve is the fine-grid solve.  Checked against the
+    oracle's element matrices at 0 local refinements + the harness' scipy solve, on 8^3 cells (device iteration for the
+    pairings beyond the dense-LU size), and the output carries the reference's names (ned_rt_ref.cc:699-730)."""
+    from common import oracle_problem
+    R = 3
+    prm, _ = _small_prm(tmp_path, pairing, L=1, g=1, std_refinements=R)
+    out = _run_driver(host_built, pairing, prm, {"MSFEC_COARSE_DENSE_LIMIT": "1000"})
+    assert "Solving >> STANDARD << problem in 3D." in out and "solver none (0 local refinements)" in out
+    assert ("on device 0" in out) == (pairing != "Q")               # Q: 729 unknowns, dense LU
+    name = EXE[pairing][6:] + "Std"
+    d = tmp_path / "out"
+    raw = np.fromfile(d / f"{name}_element_matrices.rank0.bin", dtype=np.uint8)
+    hdr = raw[:32].view(np.int64)
+    n, k = int(hdr[0]), int(hdr[1])
+    assert n == 8 ** R
+    el = raw[32:].view(np.float64).reshape(n, k * k + k)
+    cells = mo.morton_cells(R)
+    prob = oracle_problem(pairing, 0)
+    Mo = np.empty((n, k, k)); ro = np.empty((n, k))
+    for c in range(n):
+        Mo[c], ro[c] = mo.build_basis(prob, cells[c], c)[:2]
+    assert rel_err(el[:, :k * k], Mo.reshape(n, -1)) < 1e-12
+    assert np.abs(el[:, k * k:] - ro).max() <= 1e-12 * max(np.abs(ro).max(), 1.0)
+    w = np.fromfile(d / f"{name}_coarse_weights.bin", dtype=np.uint8)[16:].view(np.float64).reshape(n, k)
+    w_ref = cs.solve_coarse(pairing, R, cells, Mo, ro)
+    assert rel_err(w, w_ref) < 1e-7
+    std_name = re.search(r"Standard method parameters.*?set filename output = (\S+)", open(prm).read(), re.S).group(1)
+    piece = ET.parse(d / f"{std_name}_n_refine-{R:02d}.0000.vtu").getroot().find("UnstructuredGrid").find("Piece")
+    assert piece.get("NumberOfCells") == str(n)
+    master = ET.parse(d / f"{std_name}_n_refine-{R:02d}.pvtu").getroot().find("PUnstructuredGrid")
+    assert [p_.get("Source") for p_ in master.findall("Piece")] == [f"{std_name}_n_refine-{R:02d}.0000.vtu"]
+    assert not list(d.glob(f"{std_name}.00000.cell-*.vtu"))          # no per-cell files for the comparator

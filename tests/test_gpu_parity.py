@@ -295,3 +295,22 @@ def test_five_local_refinements_direct(msfec, pairing):
         assert np.abs(M[:, :k0, k0:] + M[:, k0:, :k0].transpose(0, 2, 1)).max() < 1e-11 * scale
     bb2 = msfec.BasisBuilder(lib_problem(msfec, pairing, 5, use_direct_solver_basis=1), device=0).run(cells[2:3], ids[2:3])
     assert np.abs(bb2.get_global_element_matrix()[0] - M[2]).max() < 1e-12 * scale
+
+
+@pytest.mark.parametrize("pairing", mo.PAIRINGS)
+def test_zero_local_refinements_give_the_standard_element_matrices(msfec, pairing):
+    """0 local refinements: no interior unknowns (RT_DQ: only the pinned one), no local solve -- the coarse matrices are the
+    standard lowest-order element matrices of the cell (what the fine-grid comparator XStd of the host driver assembles);
+    against the oracle, rough random field and sine coefficients, ragged batch."""
+    cells = mo.morton_cells(2)[:45]
+    ids = np.arange(45)
+    for seed in (0, 20261017):
+        prob = oracle_problem(pairing, 0, random_seed=seed)
+        bb = msfec.BasisBuilder(lib_problem(msfec, pairing, 0, random_seed=seed), device=0).run(cells, ids)
+        assert bb.stats["solver"] == 3 and bb.stats["not_converged"] == 0
+        M = bb.get_global_element_matrix(); r = bb.get_global_element_rhs()
+        for c in (0, 17, 44):
+            Mo, ro = mo.build_basis(prob, cells[c], c)[:2]
+            assert rel_err(M[c], Mo) < 1e-12
+            assert np.abs(r[c] - ro).max() <= 1e-12 * max(np.abs(ro).max(), 1.0)
+        bb.close()

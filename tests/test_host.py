@@ -134,7 +134,7 @@ def test_no_cpu_fallback(msfec):
 
 def test_invalid_arguments(msfec):
     p = lib_problem(msfec, "Q", 1)
-    p.n_refine_local = 0
+    p.n_refine_local = -1          # 0 is valid: the standard basis (fine-grid comparator of the host driver)
     with pytest.raises(msfec.MsfecError) as e:
         msfec.BasisBuilder(p, device=-1)
     assert e.value.code == 1
