@@ -137,8 +137,12 @@ def test_driver_two_ranks_over_nccl(msfec, host_built, tmp_path):
     prm2, _ = _small_prm(tmp_path / "b", "NED_RT")
     one = _run_driver(host_built, "NED_RT", prm1, {})
     two = _run_driver(host_built, "NED_RT", prm2, {"NCCL_DEBUG": "WARN"}, nproc=2)
-    assert "NCCL communicator over 2 rank(s)" in two
+    assert "NCCL communicator over 2 rank(s)" in two and two.count("NCCL communicator over") == 1   # one communicator for both runs
     assert np.allclose(_norms(two), _norms(one), rtol=1e-10, atol=0)
+    # the fine-grid comparator ran on both ranks too (its element matrices through the same ncclAllGather)
+    std = lambda out: np.array([float(x) for x in re.findall(r"= ([0-9.e+-]+)", [l for l in out.splitlines() if "Standard solution norms" in l][0])])
+    assert "Solving >> STANDARD << problem in 3D." in two
+    assert np.allclose(std(two), std(one), rtol=1e-10, atol=1e-12 * std(one).max())
     d = tmp_path / "b" / "out"
     assert len(list(d.glob(f"{fname}.00000.cell-*.vtu"))) == 32 and len(list(d.glob(f"{fname}.00001.cell-*.vtu"))) == 32
     master = ET.parse(d / f"{fname}_n_refine-02.pvtu").getroot().find("PUnstructuredGrid")
