@@ -51,7 +51,9 @@ enum msfec_error {
  * (eqn_coeff_B.cc:22-70) and RightHandSideParsed (eqn_rhs.cc:58-88). */
 typedef struct msfec_problem {
   int32_t pairing;               /* enum msfec_pairing                               */
-  int32_t n_refine_local;        /* "local refinements": n = 2^L fine cells per axis */
+  int32_t n_refine_local;        /* "local refinements": n = 2^L fine cells per axis, L in [0, 6].  L = 0: the cell is its own
+                                    fine grid, nothing is solved and the coarse matrices are the STANDARD lowest-order
+                                    element matrices (the fine-grid comparator of the host driver, ned_rt_ref.cc)        */
   int32_t n_refine_global;       /* "global refinements" (host driver only)          */
   int32_t use_direct_solver_basis; /* "use direct solver basis"                      */
   int32_t verbose_basis;         /* "verbose basis"                                  */

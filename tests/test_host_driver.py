@@ -115,3 +115,23 @@ def test_coarse_device_solver_exports_and_fails_loudly_without_gpu(host_built):
         assert b"no CUDA device" in lib.msfec_coarse_last_error()
     assert lib.msfec_coarse_solve_device(0, None, None, None, None, b, None, 1e-13, 1e-11, x, None, None) != 0
     assert b"null argument" in lib.msfec_coarse_last_error()
+
+
+def test_driver_reads_both_method_sections(host_built, tmp_path):
+    """`Standard method parameters` (fine-grid comparator, run first) and `Multiscale method parameters` are both read as in the
+    reference's main (main_ned_rt.cxx:66-82); with `compute solution = false` each run says so and returns
+    (ned_rt_ref.cc:736-742, ned_rt_global.cc:707-713) -- no GPU needed.  A malformed comparator section is an error."""
+    src = open(os.path.join(ROOT, "examples", "prm", "prm_ned_rt_test-01.prm")).read()
+    assert src.count("set compute solution = true") == 2
+    exe = os.path.join(host_built, "MsFEC_Ned_RT")
+    off = tmp_path / "off.prm"
+    off.write_text(src.replace("set compute solution = true", "set compute solution = false"))
+    r = subprocess.run([exe, "-p", str(off)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    a = r.stdout.index("Run of standard problem is explicitly disabled in parameter file.")
+    b = r.stdout.index("Run of multiscale problem is explicitly disabled in parameter file.")
+    assert a < b
+    bad = tmp_path / "bad.prm"
+    bad.write_text(src.replace("set refinements = 6", "set refinements = many"))
+    r = subprocess.run([exe, "-p", str(bad)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and "Standard method parameters/Mesh/refinements" in r.stderr
