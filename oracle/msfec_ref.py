@@ -1,5 +1,7 @@
 """ctypes binding of oracle/_ref/libmsfec_ref.so: the REFERENCE's own closed-form data classes (Diffusion_A,
-DiffusionInverse_A, ReactionRate, BasisQ1<3>, BasisQ1Grad<3>), compiled unmodified from /root/reference against the
+DiffusionInverse_A, ReactionRate, BasisQ1<3>, BasisQ1Grad<3>, MyMappingQ1<3>, BasisNedelec<3>, BasisRaviartThomas<3> -- the last
+two with stand-in unit-cell shape functions, i.e. what is the reference's there is the mapping and the covariant / Piola
+transform), compiled unmodified from /root/reference against the
 stand-in deal.II headers in oracle/ref_shim (oracle/Makefile).  TEST INFRASTRUCTURE ONLY: used by
 tests/test_reference_compiled.py and tests/golden/make_reference_compiled_golden.py to pin the Python oracle."""
 import ctypes
@@ -26,6 +28,8 @@ def lib():
         _lib.msfec_ref_reaction_rate.argtypes = [ctypes.c_int, _dp, _dp]
         _lib.msfec_ref_basis_q1.argtypes = [_dp, ctypes.c_int, ctypes.c_int, _dp, _dp]
         _lib.msfec_ref_basis_q1_grad.argtypes = [_dp, ctypes.c_int, ctypes.c_int, _dp, _dp]
+        _lib.msfec_ref_mapping.argtypes = [_dp, ctypes.c_int, _dp, _dp, _dp]
+        _lib.msfec_ref_basis_vector.argtypes = [_dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, _dp, _dp]
     return _lib
 
 
@@ -67,3 +71,25 @@ def basis_q1(vertices, pts):
         _check(lib().msfec_ref_basis_q1_grad(_p(vertices), i, len(pts), _p(pts), _p(g)))
         val[:, i] = v; grad[:, i, :] = g
     return val, grad
+
+
+def mapping(vertices, pts):
+    """MyMappingQ1<3> (my_mapping_q1.tpp) of the cell: unit-cell coordinates [n,3] and the Jacobian of real -> unit [n,3,3]."""
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(8, 3)
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    ref = np.empty((len(pts), 3)); jac = np.empty((len(pts), 3, 3))
+    _check(lib().msfec_ref_mapping(_p(vertices), len(pts), _p(pts), _p(ref), _p(jac)))
+    return ref, jac
+
+
+def basis_vector(vertices, kind, pts, pointwise=False):
+    """BasisNedelec<3> (kind 'ned', 12 functions) / BasisRaviartThomas<3> (kind 'rt', 6) on the cell at pts[n,3] -> [n, 12|6, 3]."""
+    vertices = np.ascontiguousarray(vertices, dtype=np.float64).reshape(8, 3)
+    pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+    nb = 12 if kind == "ned" else 6
+    out = np.empty((len(pts), nb, 3))
+    for i in range(nb):
+        v = np.empty((len(pts), 3))
+        _check(lib().msfec_ref_basis_vector(_p(vertices), 0 if kind == "ned" else 1, i, 0 if pointwise else 1, len(pts), _p(pts), _p(v)))
+        out[:, i, :] = v
+    return out

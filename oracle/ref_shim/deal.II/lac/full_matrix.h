@@ -1,5 +1,6 @@
 #pragma once
 #include <deal.II/base/shim_common.h>
+#include <deal.II/lac/vector.h>
 namespace dealii {
 template <typename Number>
 class FullMatrix {
@@ -8,6 +9,23 @@ class FullMatrix {
   FullMatrix(std::size_t m, std::size_t n) : m_(m), n_(n), a_(m * n, Number(0)) {}
   Number &operator()(std::size_t i, std::size_t j) { return a_[i * n_ + j]; }
   const Number &operator()(std::size_t i, std::size_t j) const { return a_[i * n_ + j]; }
+  FullMatrix &operator=(Number s) { for (auto &x : a_) x = s; return *this; }
+  // w = A v,  w = A^T v
+  void vmult(Vector<Number> &w, const Vector<Number> &v) const {
+    for (std::size_t i = 0; i < m_; ++i) { Number s = 0; for (std::size_t j = 0; j < n_; ++j) s += (*this)(i, j) * v(j); w(i) = s; }
+  }
+  void Tvmult(Vector<Number> &w, const Vector<Number> &v) const {
+    for (std::size_t j = 0; j < n_; ++j) { Number s = 0; for (std::size_t i = 0; i < m_; ++i) s += (*this)(i, j) * v(i); w(j) = s; }
+  }
+  Number determinant() const {
+    const FullMatrix &A = *this;
+    if (m_ == 1 && n_ == 1) return A(0, 0);
+    if (m_ == 2 && n_ == 2) return A(0, 0) * A(1, 1) - A(0, 1) * A(1, 0);
+    if (m_ == 3 && n_ == 3)
+      return A(0, 0) * (A(1, 1) * A(2, 2) - A(1, 2) * A(2, 1)) - A(0, 1) * (A(1, 0) * A(2, 2) - A(1, 2) * A(2, 0)) +
+             A(0, 2) * (A(1, 0) * A(2, 1) - A(1, 1) * A(2, 0));
+    throw std::runtime_error("FullMatrix::determinant: only up to 3 x 3");
+  }
   std::size_t m() const { return m_; }
   std::size_t n() const { return n_; }
   // *this = M^-1 (Gauss-Jordan with partial pivoting)

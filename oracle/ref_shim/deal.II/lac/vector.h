@@ -9,6 +9,7 @@ class Vector {
   Number &operator()(std::size_t i) { return v_[i]; }
   const Number &operator()(std::size_t i) const { return v_[i]; }
   Vector &operator=(Number s) { for (auto &x : v_) x = s; return *this; }
+  Vector &operator/=(Number s) { for (auto &x : v_) x /= s; return *this; }
   std::size_t size() const { return v_.size(); }
  private:
   std::vector<Number> v_;

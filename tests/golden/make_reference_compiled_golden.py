@@ -38,5 +38,9 @@ rng = np.random.default_rng(20261018)
 pts = x0 + H * rng.random((64, 3))
 val, grad = mr.basis_q1(vertices, pts)
 out.update(q1_x0=x0, q1_H=np.array(H), q1_pts=pts, q1_val=val, q1_grad=grad)
+# the same cube: the reference's Q1 mapping and its covariant (Nedelec) / Piola (Raviart-Thomas) transforms; the unit-cell shape
+# functions under them are stand-ins (oracle/ref_shim/deal.II/fe), so what these arrays pin is the H-scaling and the mapping
+ref, jac = mr.mapping(vertices, pts)
+out.update(map_ref=ref, map_inv_jac=jac, ned_val=mr.basis_vector(vertices, "ned", pts), rt_val=mr.basis_vector(vertices, "rt", pts))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "reference_compiled_eqdata.npz"), **out)
 print("wrote", len(out), "arrays")

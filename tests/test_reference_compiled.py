@@ -47,6 +47,22 @@ def test_oracle_coarse_q1_matches_compiled_reference_golden():
     assert np.abs(grad - gold["q1_grad"]).max() <= 1e-12 * np.abs(gold["q1_grad"]).max()
 
 
+def test_oracle_coarse_nedelec_and_rt_scaling_matches_compiled_reference_golden():
+    """MyMappingQ1 + BasisNedelec / BasisRaviartThomas of the reference (compiled; the unit-cell shape functions under them are
+    stand-ins restating deal.II's documented lowest-order elements): the mapping to the unit cell, its Jacobian 1/H, and the
+    transforms J^-T phi (Nedelec, 1/H) and J phi / det J (Raviart-Thomas, 1/H^2) that scale the boundary data of the local
+    problems (a4) -- against the oracle's coarse_ned / coarse_rt on a non-unit cube."""
+    gold = np.load(GOLD)
+    x0, H, pts = gold["q1_x0"], float(gold["q1_H"]), gold["q1_pts"]
+    assert np.abs((pts - x0) / H - gold["map_ref"]).max() < 1e-12
+    assert np.abs(gold["map_inv_jac"] - np.eye(3) / H).max() < 1e-10 / H
+    ned, _ = mo.coarse_ned(x0, H, pts)
+    rt, _ = mo.coarse_rt(x0, H, pts)
+    assert np.abs(ned - gold["ned_val"]).max() <= 1e-11 * np.abs(gold["ned_val"]).max()
+    assert np.abs(rt - gold["rt_val"]).max() <= 1e-11 * np.abs(gold["rt_val"]).max()
+    assert np.abs(gold["ned_val"]).max() > 0.9 / H and np.abs(gold["rt_val"]).max() > 0.9 / H ** 2   # the scaling is exercised
+
+
 @pytest.mark.skipif(not mr.available(), reason="oracle/_ref/libmsfec_ref.so not built (needs /root/reference)")
 def test_oracle_matches_compiled_reference_live():
     rng = np.random.default_rng(7)
@@ -70,6 +86,13 @@ def test_oracle_matches_compiled_reference_live():
     assert np.abs(mv - val).max() <= 1e-12 and np.abs(mg - grad).max() <= 1e-12 * np.abs(grad).max()
     # Kronecker property at the vertices: pins the vertex order the oracle's q1_ref assumes
     assert np.abs(mr.basis_q1(vertices, vertices)[0] - np.eye(8)).max() < 1e-12
+    # mapping and the covariant / Piola transforms, value() and value_list() paths
+    ref, jac = mr.mapping(vertices, p)
+    assert np.abs(ref - (p - x0) / H).max() < 1e-12 and np.abs(jac - np.eye(3) / H).max() < 1e-10 / H
+    for kind, mine in (("ned", mo.coarse_ned(x0, H, p)[0]), ("rt", mo.coarse_rt(x0, H, p)[0])):
+        for pointwise in (False, True):
+            theirs = mr.basis_vector(vertices, kind, p, pointwise=pointwise)
+            assert np.abs(mine - theirs).max() <= 1e-11 * np.abs(theirs).max()
 
 
 def test_compiled_reference_reads_a_missing_prm_loudly():
